@@ -1,0 +1,169 @@
+// common.cuh — device-side data layout of one launch batch (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr int R_COLS = 31;        // TOP_K_SORT + 1 (src/features.rs:22)
+constexpr int ROW_BYTES = 32;     // internal row pitch of the [L',31] matrices (col 31 = pad)
+constexpr int TOP_K = 30;
+constexpr int MAX_COLS = 1024;    // overlap-windows per window handled on-chip (error beyond)
+
+constexpr uint32_t TOK_GAP_F = 4, TOK_GAP_R = 9, TOK_NONE = 10, TOK_PAD = 11;  // src/inference.rs:15,23-31
+constexpr uint8_t QUAL_EMPTY = 33;    // '!' src/features.rs:283
+constexpr uint8_t QUAL_PAD = 126;     // QUAL_MAX_VAL src/inference.rs:17,93-97
+
+constexpr uint32_t OWF_LONG_INDEL = 1;  // src/features.rs:315-324
+constexpr uint32_t OWF_BAD = 2;         // input on which the reference would panic
+
+constexpr uint32_t OP_M = 0, OP_I = 2, OP_D = 3;
+
+struct DevOverlap {  // Overlap (src/overlaps.rs:44-55) reduced to what the path reads
+    uint32_t qid, qstart, qend, strand;
+    uint64_t cig_off;
+    uint32_t cig_len;
+    uint32_t tgt;  // target index inside the batch
+};
+
+struct DevOW {  // OverlapWindow (src/windowing.rs:6-16)
+    uint32_t ovl;  // batch-global overlap index
+    uint32_t win;  // batch-global window index
+    uint32_t tstart, qstart, qend;
+    uint32_t csi, cso, cei, ceo;
+    uint32_t op_base;  // first slot in the tokenised-op arrays
+};
+
+struct DevWin {
+    uint32_t tgt, rid, wid;
+    uint32_t tstart;  // wid * W
+    uint32_t len;     // W, or the remainder for the last window (src/features.rs:369-373)
+    uint32_t ow_begin, ow_end;
+    uint32_t pad;
+};
+
+struct DevTarget {
+    uint32_t rid, win_begin, win_end, ovl_begin, ovl_end;
+};
+
+struct ReadStoreView {
+    const uint64_t* words;     // all reads, 2-bit packed (src/haec_io.rs:121-136)
+    const uint64_t* word_off;  // [n+1]
+    const uint32_t* len;       // [n]
+    const uint8_t* qual;       // all reads, raw bytes
+    const uint64_t* qual_off;  // [n+1]
+    uint32_t n;
+};
+
+// Everything a feature/consensus kernel needs, passed by value.
+struct BatchView {
+    ReadStoreView rs;
+    uint32_t W;  // window size
+    uint32_t n_tgt, n_win, n_ovl, n_ow;
+    uint32_t batch_size;  // reference `-b`
+    // inputs
+    const DevTarget* tgt;
+    const DevWin* win;
+    const DevOverlap* ovl;
+    const DevOW* ow;
+    const uint8_t* cig;
+    // tokenised ops
+    uint32_t* op_kl;  // kind | eff_len << 2
+    uint32_t* op_t;   // window-relative target position at op start
+    uint32_t* op_q;   // oriented-query offset at op start
+    // per overlap-window
+    uint32_t* ow_nops;
+    uint32_t* ow_flags;
+    float* ow_acc;
+    uint32_t* ow_tend;  // window-relative target position after the last op
+    // per window, pass 1
+    uint32_t* col_ow;  // [n_ow] first-pass column order (CSR with win.ow_begin)
+    uint32_t* w_n1;    // columns surviving the filter
+    uint32_t* w_S;     // first-pass supported base rows
+    // per overlap (= per query read of a target)
+    uint32_t* ovl_n;
+    uint32_t* ovl_tot;
+    double* ovl_score;
+    const double* ln_table;  // ln(k) computed by the host libm, k < ln_table_n
+    uint32_t ln_table_n;
+    // per window, pass 2
+    uint32_t* sel_ow;   // [n_win * 30]
+    uint32_t* w_nsel;   // n_alns
+    uint32_t* rowmap;   // [n_win * (W+1)]: row'(p), last = L'
+    uint32_t* w_L;      // L'
+    uint64_t* w_rowbase;
+    uint32_t* w_nsup;
+    uint32_t* w_reflmax;  // Lmax of the reference batch this window would be collated into
+    uint64_t rows_cap;
+    // matrices (row pitch 32)
+    uint8_t* mat_bases;
+    uint8_t* mat_quals;
+    uint8_t* row_emit;   // class 0..4 to emit for the row (4 = nothing) | 0x80 if supported
+    uint32_t* sup_row;   // [rows_cap] per window at w_rowbase: row index of k-th supported row
+    uint32_t* sup_pk;    // (pos << 8) | ins
+    // flattened forward work list
+    uint64_t* w_supbase;  // exclusive scan of w_nsup
+    uint32_t* fwd_win;    // [n_sup_total]
+    uint32_t* fwd_row;    // row inside window
+    // consensus
+    uint32_t* w_outlen;
+    uint64_t* w_outoff;
+    uint8_t* out_bytes;
+    // status
+    uint32_t* tgt_err;   // per target: OR of problems
+    uint32_t* counters;  // [0] total rows overflow flag, [1] n_sup_total, [2] total_out, [3] total_rows lo, ...
+};
+
+constexpr int CNT_OVERFLOW = 0, CNT_TOTAL_ROWS = 2, CNT_TOTAL_OUT = 4, CNT_NSUP = 6, CNT_N = 8;  // 64-bit totals use 2 slots
+
+constexpr uint32_t TERR_BAD_INPUT = 1, TERR_TOO_MANY_COLS = 2;
+
+#define HB_FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t code_at(const uint64_t* __restrict__ w, uint32_t i) {
+    return (uint32_t)(__ldg(w + (i >> 5)) >> ((i & 31u) << 1)) & 3u;
+}
+
+// View of the (strand-oriented) query slice of one overlap-window — src/features.rs:97-108,122-153
+struct QView {
+    const uint64_t* words;
+    const uint8_t* qual;
+    uint32_t qs, qe;
+    uint32_t rev;
+    __device__ __forceinline__ uint32_t code(uint32_t x) const {
+        return rev ? (code_at(words, qe - 1u - x) ^ 3u) : code_at(words, qs + x);
+    }
+    __device__ __forceinline__ uint8_t q(uint32_t x) const { return rev ? __ldg(qual + (qe - 1u - x)) : __ldg(qual + qs + x); }
+};
+
+__device__ __forceinline__ QView make_qview(const ReadStoreView& rs, const DevOverlap& ov, const DevOW& ow) {
+    QView v;
+    v.words = rs.words + rs.word_off[ov.qid];
+    v.qual = rs.qual + rs.qual_off[ov.qid];
+    v.rev = ov.strand;
+    if (!ov.strand) {
+        v.qs = ov.qstart + ow.qstart;
+        v.qe = ov.qstart + ow.qend;
+    } else {
+        v.qs = ov.qend - ow.qend;
+        v.qe = ov.qend - ow.qstart;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HB_FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(HB_FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace hb

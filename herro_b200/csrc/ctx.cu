@@ -1,0 +1,883 @@
+// ctx.cu — hb_ctx: the C ABI of include/herro_b200.h on top of the kernels in features.cu /
+// forward.cu.  Host-side responsibilities: replicate the read store, stage target batches
+// (cross-read batching: the reference launches one tiny forward per read, src/features.rs:582,
+// SURVEY.md F7), drive the kernel sequence on a stream, and re-assemble per-read segments
+// the way consensus() does (src/consensus.rs:86-111,222-226).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/herro_b200.h"
+#include "common.cuh"
+#include "forward.h"
+#include "windowing.h"
+
+using namespace hb;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice);
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t ncap = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, ncap);
+        if (e == cudaSuccess) cap = ncap;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct HostBatch {
+    std::vector<DevTarget> tgt;
+    std::vector<DevWin> win;
+    std::vector<DevOverlap> ovl;
+    std::vector<DevOW> ow;
+    std::vector<uint8_t> cig;
+    uint64_t op_cap = 0;
+    void clear() { tgt.clear(); win.clear(); ovl.clear(); ow.clear(); cig.clear(); op_cap = 0; }
+};
+
+struct Result {
+    uint32_t rid;
+    int status;
+    std::vector<uint32_t> seg_len;
+    std::vector<uint8_t> seq;
+};
+
+struct LastLaunch {  // host copies of per-window metadata of the most recent launch (debug taps / replay)
+    bool valid = false;
+    std::vector<DevWin> win;
+    std::vector<uint32_t> w_L, w_nsel, w_nsup;
+    std::vector<uint64_t> w_rowbase, w_supbase;
+    std::unordered_map<uint64_t, uint32_t> index;  // (rid << 32 | wid) -> window
+    uint64_t n_sup = 0, total_rows = 0;
+    BatchView view;
+};
+
+}  // namespace
+
+struct hb_ctx {
+    int device = 0;
+    hb_options opt{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8]{};
+    std::string err;
+    std::mutex mu;
+
+    // weights
+    FwdWeights wt{};
+    std::vector<void*> weight_allocs;
+
+    // read store
+    bool have_reads = false;
+    uint32_t n_reads = 0;
+    std::vector<uint32_t> read_len;
+    DevBuf d_words, d_word_off, d_len, d_qual, d_qual_off, d_ln;
+    uint32_t ln_n = 0;
+    ReadStoreView rs{};
+
+    // staging
+    HostBatch hbatch;
+    PinBuf pin_in, pin_small, pin_out;
+    DevBuf d_tgt, d_win, d_ovl, d_ow, d_cig;
+    DevBuf d_op_kl, d_op_t, d_op_q, d_ow_nops, d_ow_flags, d_ow_acc, d_ow_tend, d_col_ow, d_w_n1, d_w_S;
+    DevBuf d_ovl_n, d_ovl_tot, d_ovl_score, d_sel_ow, d_w_nsel, d_rowmap, d_w_L, d_w_rowbase, d_w_nsup, d_w_reflmax;
+    DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
+    DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info;
+    uint64_t rows_cap = 0;
+    uint32_t chunk_pos = 8192;
+
+    std::deque<Result> results;
+    std::unordered_map<uint8_t*, void*> live;  // seqs pointer -> malloc block
+    hb_stats stats{};
+    LastLaunch last;
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);           \
+            return HB_ERR_CUDA;                                                       \
+        }                                                                             \
+    } while (0)
+
+int fail(hb_ctx* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------- weights
+#pragma pack(push, 1)
+struct BlobHeader {
+    char magic[8];
+    uint32_t version, n_tensors;
+    uint32_t cfg[16];
+};
+struct BlobEntry {
+    char name[48];
+    uint32_t dtype, ndim, shape[4];
+    uint64_t offset, nbytes;
+};
+#pragma pack(pop)
+
+int load_weights(hb_ctx* ctx, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, HB_ERR_MODEL, std::string("cannot open model file ") + path);
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf((size_t)sz);
+    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(ctx, HB_ERR_MODEL, "short read on model file"); }
+    fclose(f);
+    if ((size_t)sz < sizeof(BlobHeader)) return fail(ctx, HB_ERR_MODEL, "model file too small");
+    BlobHeader h;
+    memcpy(&h, buf.data(), sizeof h);
+    if (memcmp(h.magic, "HB200W1\0", 8) != 0 || h.version != 1)
+        return fail(ctx, HB_ERR_MODEL, "not an HB200W1 weights blob (convert TorchScript archives with tools/export_weights.py)");
+    if (h.cfg[0] != 12 || h.cfg[1] != 6 || h.cfg[2] != 31 || h.cfg[9] != 5)
+        return fail(ctx, HB_ERR_MODEL, "unsupported fixed dimensions (tokens/emb/reads/classes)");
+    FwdWeights& wt = ctx->wt;
+    wt.stem_k = (int)h.cfg[3]; wt.C = (int)h.cfg[4]; wt.H = (int)h.cfg[5]; wt.layers = (int)h.cfg[6];
+    wt.F = (int)h.cfg[7]; wt.D = (int)h.cfg[8];
+    if (wt.layers < 1 || wt.layers > MAX_LAYERS || wt.H < 1 || wt.C % wt.H || (wt.C / wt.H != 16 && wt.C / wt.H != 32) ||
+        wt.C % 64 || wt.F % 64 || wt.D % 64 || !(wt.stem_k & 1) || wt.stem_k > 129 || wt.C > 1024)
+        return fail(ctx, HB_ERR_MODEL, "unsupported model dimensions (need C,F,D % 64 == 0, head_dim 16 or 32, odd stem_k)");
+    std::unordered_map<std::string, std::pair<const float*, size_t>> T;
+    for (uint32_t i = 0; i < h.n_tensors; i++) {
+        BlobEntry e;
+        size_t eo = sizeof(BlobHeader) + (size_t)i * sizeof(BlobEntry);
+        if (eo + sizeof e > (size_t)sz) return fail(ctx, HB_ERR_MODEL, "truncated tensor table");
+        memcpy(&e, buf.data() + eo, sizeof e);
+        if (e.dtype != 0 || e.offset + e.nbytes > (uint64_t)sz) return fail(ctx, HB_ERR_MODEL, "bad tensor entry");
+        char nm[49];
+        memcpy(nm, e.name, 48);
+        nm[48] = 0;
+        T[nm] = {(const float*)(buf.data() + e.offset), (size_t)(e.nbytes / 4)};
+    }
+    auto need = [&](const std::string& n, size_t count, const float*& hostp) -> bool {
+        auto it = T.find(n);
+        if (it == T.end() || it->second.second != count) { ctx->err = "missing/mis-sized tensor " + n; return false; }
+        hostp = it->second.first;
+        return true;
+    };
+    auto upload = [&](const float* hostp, size_t count, const float*& devp) -> bool {
+        void* d = nullptr;
+        if (cudaMalloc(&d, count * 4) != cudaSuccess) { ctx->err = "cudaMalloc(weights)"; return false; }
+        ctx->weight_allocs.push_back(d);
+        if (cudaMemcpy(d, hostp, count * 4, cudaMemcpyHostToDevice) != cudaSuccess) { ctx->err = "cudaMemcpy(weights)"; return false; }
+        devp = (const float*)d;
+        return true;
+    };
+    auto get = [&](const std::string& n, size_t count, const float*& devp) -> bool {
+        const float* hp;
+        return need(n, count, hp) && upload(hp, count, devp);
+    };
+    const int C = wt.C, K = wt.stem_k, F = wt.F, D = wt.D;
+    const float *emb, *stem_w;
+    if (!need("emb", 12 * 6, emb) || !need("stem_w", (size_t)C * 7 * K, stem_w)) return HB_ERR_MODEL;
+    // fold the embedding into the conv: tab[j][t][c] = sum_e stem_w[c][e][j] * emb[t][e]
+    std::vector<float> tab((size_t)K * 12 * C), wq((size_t)K * C);
+    for (int j = 0; j < K; j++)
+        for (int c = 0; c < C; c++) {
+            for (int t = 0; t < 12; t++) {
+                float acc = 0.f;  // fp32, e ascending: the order a direct conv over 7 input channels would use
+                for (int e = 0; e < 6; e++) acc = fmaf(stem_w[((size_t)c * 7 + e) * K + j], emb[t * 6 + e], acc);
+                tab[((size_t)j * 12 + t) * C + c] = acc;
+            }
+            wq[(size_t)j * C + c] = stem_w[((size_t)c * 7 + 6) * K + j];
+        }
+    if (!upload(tab.data(), tab.size(), wt.stem_tab) || !upload(wq.data(), wq.size(), wt.stem_wq)) return HB_ERR_CUDA;
+    bool ok = get("stem_b", C, wt.stem_b) && get("read_pos", 31 * (size_t)C, wt.read_pos);
+    for (int l = 0; ok && l < wt.layers; l++) {
+        const std::string p = "l" + std::to_string(l) + ".";
+        FwdLayer& ly = wt.layer[l];
+        ok = get(p + "ln1_g", C, ly.ln1_g) && get(p + "ln1_b", C, ly.ln1_b) && get(p + "wqkv", (size_t)3 * C * C, ly.wqkv) &&
+             get(p + "bqkv", 3 * (size_t)C, ly.bqkv) && get(p + "wo", (size_t)C * C, ly.wo) && get(p + "bo", C, ly.bo) &&
+             get(p + "ln2_g", C, ly.ln2_g) && get(p + "ln2_b", C, ly.ln2_b) && get(p + "w1", (size_t)F * C, ly.w1) &&
+             get(p + "b1", F, ly.b1) && get(p + "w2", (size_t)C * F, ly.w2) && get(p + "b2", C, ly.b2);
+    }
+    ok = ok && get("lnf_g", C, wt.lnf_g) && get("lnf_b", C, wt.lnf_b) && get("wc", (size_t)D * 31 * C, wt.wc) &&
+         get("bc", D, wt.bc) && get("wb", 5 * (size_t)D, wt.wb) && get("bb", 5, wt.bb) && get("wi", D, wt.wi) &&
+         get("bi", 1, wt.bi);
+    if (!ok) return ctx->err.rfind("cuda", 0) == 0 ? HB_ERR_CUDA : HB_ERR_MODEL;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------- batch run
+template <class T>
+size_t vbytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
+
+int ensure_batch_buffers(hb_ctx* ctx, const HostBatch& hbt) {
+    const size_t nt = hbt.tgt.size(), nw = hbt.win.size(), no = hbt.ovl.size(), now_ = hbt.ow.size();
+    const uint32_t W = ctx->opt.window_size;
+    CK(ctx->d_tgt.ensure(nt * sizeof(DevTarget)));
+    CK(ctx->d_win.ensure(nw * sizeof(DevWin)));
+    CK(ctx->d_ovl.ensure(std::max<size_t>(no, 1) * sizeof(DevOverlap)));
+    CK(ctx->d_ow.ensure(std::max<size_t>(now_, 1) * sizeof(DevOW)));
+    CK(ctx->d_cig.ensure(std::max<size_t>(hbt.cig.size(), 16)));
+    const size_t opc = std::max<uint64_t>(hbt.op_cap, 1);
+    CK(ctx->d_op_kl.ensure(opc * 4));
+    CK(ctx->d_op_t.ensure(opc * 4));
+    CK(ctx->d_op_q.ensure(opc * 4));
+    const size_t ow1 = std::max<size_t>(now_, 1);
+    CK(ctx->d_ow_nops.ensure(ow1 * 4));
+    CK(ctx->d_ow_flags.ensure(ow1 * 4));
+    CK(ctx->d_ow_acc.ensure(ow1 * 4));
+    CK(ctx->d_ow_tend.ensure(ow1 * 4));
+    CK(ctx->d_col_ow.ensure(ow1 * 4));
+    CK(ctx->d_w_n1.ensure(nw * 4));
+    CK(ctx->d_w_S.ensure(nw * 4));
+    const size_t no1 = std::max<size_t>(no, 1);
+    CK(ctx->d_ovl_n.ensure(no1 * 4));
+    CK(ctx->d_ovl_tot.ensure(no1 * 4));
+    CK(ctx->d_ovl_score.ensure(no1 * 8));
+    CK(ctx->d_sel_ow.ensure(nw * TOP_K * 4));
+    CK(ctx->d_w_nsel.ensure(nw * 4));
+    CK(ctx->d_rowmap.ensure(nw * (size_t)(W + 1) * 4));
+    CK(ctx->d_w_L.ensure(nw * 4));
+    CK(ctx->d_w_rowbase.ensure(nw * 8));
+    CK(ctx->d_w_nsup.ensure(nw * 4));
+    CK(ctx->d_w_reflmax.ensure(nw * 4));
+    CK(ctx->d_w_supbase.ensure(nw * 8));
+    CK(ctx->d_w_outlen.ensure(nw * 4));
+    CK(ctx->d_w_outoff.ensure(nw * 8));
+    CK(ctx->d_tgt_err.ensure(nt * 4));
+    CK(ctx->d_counters.ensure(CNT_N * 4));
+    return HB_OK;
+}
+
+int ensure_row_buffers(hb_ctx* ctx, uint64_t rows) {
+    if (rows <= ctx->rows_cap) return HB_OK;
+    CK(ctx->d_mat_b.ensure(rows * ROW_BYTES));
+    CK(ctx->d_mat_q.ensure(rows * ROW_BYTES));
+    CK(ctx->d_row_emit.ensure(rows));
+    CK(ctx->d_sup_row.ensure(rows * 4));
+    CK(ctx->d_sup_pk.ensure(rows * 4));
+    CK(ctx->d_out.ensure(rows));
+    ctx->rows_cap = rows;
+    return HB_OK;
+}
+
+BatchView make_view(hb_ctx* ctx, const HostBatch& hbt) {
+    BatchView b{};
+    b.rs = ctx->rs;
+    b.W = ctx->opt.window_size;
+    b.n_tgt = (uint32_t)hbt.tgt.size();
+    b.n_win = (uint32_t)hbt.win.size();
+    b.n_ovl = (uint32_t)hbt.ovl.size();
+    b.n_ow = (uint32_t)hbt.ow.size();
+    b.batch_size = ctx->opt.batch_size;
+    b.tgt = ctx->d_tgt.as<DevTarget>();
+    b.win = ctx->d_win.as<DevWin>();
+    b.ovl = ctx->d_ovl.as<DevOverlap>();
+    b.ow = ctx->d_ow.as<DevOW>();
+    b.cig = ctx->d_cig.as<uint8_t>();
+    b.op_kl = ctx->d_op_kl.as<uint32_t>();
+    b.op_t = ctx->d_op_t.as<uint32_t>();
+    b.op_q = ctx->d_op_q.as<uint32_t>();
+    b.ow_nops = ctx->d_ow_nops.as<uint32_t>();
+    b.ow_flags = ctx->d_ow_flags.as<uint32_t>();
+    b.ow_acc = ctx->d_ow_acc.as<float>();
+    b.ow_tend = ctx->d_ow_tend.as<uint32_t>();
+    b.col_ow = ctx->d_col_ow.as<uint32_t>();
+    b.w_n1 = ctx->d_w_n1.as<uint32_t>();
+    b.w_S = ctx->d_w_S.as<uint32_t>();
+    b.ovl_n = ctx->d_ovl_n.as<uint32_t>();
+    b.ovl_tot = ctx->d_ovl_tot.as<uint32_t>();
+    b.ovl_score = ctx->d_ovl_score.as<double>();
+    b.ln_table = ctx->d_ln.as<double>();
+    b.ln_table_n = ctx->ln_n;
+    b.sel_ow = ctx->d_sel_ow.as<uint32_t>();
+    b.w_nsel = ctx->d_w_nsel.as<uint32_t>();
+    b.rowmap = ctx->d_rowmap.as<uint32_t>();
+    b.w_L = ctx->d_w_L.as<uint32_t>();
+    b.w_rowbase = ctx->d_w_rowbase.as<uint64_t>();
+    b.w_nsup = ctx->d_w_nsup.as<uint32_t>();
+    b.w_reflmax = ctx->d_w_reflmax.as<uint32_t>();
+    b.rows_cap = ctx->rows_cap;
+    b.mat_bases = ctx->d_mat_b.as<uint8_t>();
+    b.mat_quals = ctx->d_mat_q.as<uint8_t>();
+    b.row_emit = ctx->d_row_emit.as<uint8_t>();
+    b.sup_row = ctx->d_sup_row.as<uint32_t>();
+    b.sup_pk = ctx->d_sup_pk.as<uint32_t>();
+    b.w_supbase = ctx->d_w_supbase.as<uint64_t>();
+    b.fwd_win = ctx->d_fwd_win.as<uint32_t>();
+    b.fwd_row = ctx->d_fwd_row.as<uint32_t>();
+    b.w_outlen = ctx->d_w_outlen.as<uint32_t>();
+    b.w_outoff = ctx->d_w_outoff.as<uint64_t>();
+    b.out_bytes = ctx->d_out.as<uint8_t>();
+    b.tgt_err = ctx->d_tgt_err.as<uint32_t>();
+    b.counters = ctx->d_counters.as<uint32_t>();
+    return b;
+}
+
+int zero_scratch(hb_ctx* ctx, const BatchView& b) {
+    CK(cudaMemsetAsync(b.ovl_n, 0, std::max<size_t>(b.n_ovl, 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.ovl_tot, 0, std::max<size_t>(b.n_ovl, 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.tgt_err, 0, (size_t)b.n_tgt * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.counters, 0, CNT_N * 4, ctx->stream));
+    return HB_OK;
+}
+
+// The forward + consensus part once the number of supported positions is known.
+int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launches) {
+    *launches += launch_features_c2(b, ctx->stream);
+    for (uint64_t n0 = 0; n0 < n_sup; n0 += ctx->chunk_pos) {
+        const uint32_t np = (uint32_t)std::min<uint64_t>(ctx->chunk_pos, n_sup - n0);
+        *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, ctx->d_ws.as<float>(), ctx->d_logits.as<float>(),
+                                          ctx->d_info.as<float>(), ctx->stream);
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    *launches += launch_consensus(b, ctx->stream);
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    return HB_OK;
+}
+
+int run_batch(hb_ctx* ctx) {
+    HostBatch& hbt = ctx->hbatch;
+    if (hbt.tgt.empty()) return HB_OK;
+    const uint32_t W = ctx->opt.window_size;
+    int rc = ensure_batch_buffers(ctx, hbt);
+    if (rc) return rc;
+    const size_t nt = hbt.tgt.size(), nw = hbt.win.size();
+    // ---- H2D through one pinned staging area
+    const size_t sz[5] = {vbytes(hbt.tgt), vbytes(hbt.win), vbytes(hbt.ovl), vbytes(hbt.ow), hbt.cig.size()};
+    size_t off[6] = {0};
+    for (int i = 0; i < 5; i++) off[i + 1] = (off[i] + sz[i] + 255) & ~(size_t)255;
+    CK(ctx->pin_in.ensure(off[5] + 256));
+    uint8_t* pin = ctx->pin_in.as<uint8_t>();
+    memcpy(pin + off[0], hbt.tgt.data(), sz[0]);
+    memcpy(pin + off[1], hbt.win.data(), sz[1]);
+    memcpy(pin + off[2], hbt.ovl.data(), sz[2]);
+    memcpy(pin + off[3], hbt.ow.data(), sz[3]);
+    memcpy(pin + off[4], hbt.cig.data(), sz[4]);
+    void* dst[5] = {ctx->d_tgt.p, ctx->d_win.p, ctx->d_ovl.p, ctx->d_ow.p, ctx->d_cig.p};
+    for (int i = 0; i < 5; i++)
+        if (sz[i]) CK(cudaMemcpyAsync(dst[i], pin + off[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
+
+    if (ctx->rows_cap == 0) { rc = ensure_row_buffers(ctx, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
+    CK(ctx->pin_small.ensure(CNT_N * 4 + nw * 4 * 4 + nt * 4 + nw * TOP_K * 4 + 1024));
+    uint32_t* h_cnt = ctx->pin_small.as<uint32_t>();
+    uint64_t launches = 0;
+    BatchView b;
+    uint64_t total_rows = 0;
+    for (int attempt = 0;; attempt++) {
+        b = make_view(ctx, hbt);
+        rc = zero_scratch(ctx, b);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        launches += launch_features_a(b, ctx->stream);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        launches += launch_pileup(b, ctx->stream);
+        CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        launches += launch_features_c1(b, ctx->stream);  // ref_lmax + scan; the work list needs its buffers first
+        CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        total_rows = (uint64_t)h_cnt[CNT_TOTAL_ROWS] | ((uint64_t)h_cnt[CNT_TOTAL_ROWS + 1] << 32);
+        if (!h_cnt[CNT_OVERFLOW]) break;
+        if (attempt >= 2) return fail(ctx, HB_ERR_CAPACITY, "row arena overflow persisted after regrowth");
+        rc = ensure_row_buffers(ctx, total_rows + total_rows / 8 + 4096);
+        if (rc) return rc;
+    }
+    const uint64_t n_sup = (uint64_t)h_cnt[CNT_NSUP] | ((uint64_t)h_cnt[CNT_NSUP + 1] << 32);
+    CK(ctx->d_fwd_win.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(ctx->d_fwd_row.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(ctx->d_logits.ensure(std::max<uint64_t>(n_sup, 1) * 5 * 4));
+    CK(ctx->d_info.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(ctx->d_ws.ensure(fwd_workspace_floats(ctx->wt, ctx->chunk_pos) * 4));
+    b = make_view(ctx, hbt);
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    rc = launch_tail(ctx, b, n_sup, &launches);
+    if (rc) return rc;
+
+    // ---- D2H: per-window metadata, then exactly the emitted bytes
+    uint32_t* h_outlen = h_cnt + CNT_N;
+    uint32_t* h_nsel = h_outlen + nw;
+    uint32_t* h_L = h_nsel + nw;
+    uint32_t* h_nsup = h_L + nw;
+    uint32_t* h_terr = h_nsup + nw;
+    uint32_t* h_sel = h_terr + nt;
+    CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_outlen, b.w_outlen, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_nsel, b.w_nsel, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_L, b.w_L, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_nsup, b.w_nsup, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_terr, b.tgt_err, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_sel, b.sel_ow, nw * TOP_K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t total_out = (uint64_t)h_cnt[CNT_TOTAL_OUT] | ((uint64_t)h_cnt[CNT_TOTAL_OUT + 1] << 32);
+    CK(ctx->pin_out.ensure(total_out + 16));
+    if (total_out) CK(cudaMemcpyAsync(ctx->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
+
+    // ---- timing
+    float ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); ctx->stats.ms_features += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_pileup_kernel += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_forward += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->stats.ms_consensus += ms;
+
+    // ---- per-read reassembly (src/consensus.rs:90-111,222-226)
+    const uint8_t* outb = ctx->pin_out.as<uint8_t>();
+    uint64_t o = 0, corrected = 0, algo = 0;
+    for (size_t t = 0; t < nt; t++) {
+        const DevTarget& tg = hbt.tgt[t];
+        Result r;
+        r.rid = tg.rid;
+        r.status = h_terr[t] ? HB_ERR_INPUT : HB_OK;
+        std::vector<uint8_t> cur;
+        for (uint32_t w = tg.win_begin; w < tg.win_end; w++) {
+            const uint32_t len = h_outlen[w];
+            if (h_nsel[w] >= 2) {
+                cur.insert(cur.end(), outb + o, outb + o + len);
+            } else if (!cur.empty()) {
+                r.seg_len.push_back((uint32_t)cur.size());
+                r.seq.insert(r.seq.end(), cur.begin(), cur.end());
+                cur.clear();
+            }
+            o += len;
+            // algorithmic bytes of the pileup build for this window (SURVEY.md §8d closed form over the
+            // 31 columns the kernel consumes)
+            const DevWin& dw = hbt.win[w];
+            uint64_t cb = 0;
+            for (uint32_t c = 0; c < h_nsel[w]; c++) {
+                const DevOW& ow = hbt.ow[h_sel[(size_t)w * TOP_K + c]];
+                cb += ow.cei - ow.csi;
+            }
+            algo += (uint64_t)(h_nsel[w] + 1) * ((dw.len + 3) / 4 + dw.len) + cb + 2ull * R_COLS * h_L[w];
+        }
+        if (!cur.empty()) {
+            r.seg_len.push_back((uint32_t)cur.size());
+            r.seq.insert(r.seq.end(), cur.begin(), cur.end());
+        }
+        if (r.status != HB_OK) { r.seg_len.clear(); r.seq.clear(); }
+        corrected += r.seq.size();
+        ctx->results.push_back(std::move(r));
+    }
+    ctx->stats.targets += nt;
+    ctx->stats.windows += nw;
+    ctx->stats.overlap_windows += hbt.ow.size();
+    ctx->stats.rows += total_rows;
+    ctx->stats.supported += n_sup;
+    ctx->stats.corrected_bases += corrected;
+    ctx->stats.kernel_launches += launches;
+    ctx->stats.device_launches += 1;
+    ctx->stats.pileup_algo_bytes += algo;
+
+    // ---- keep metadata for the debug taps / replay
+    LastLaunch& ll = ctx->last;
+    ll.valid = true;
+    ll.win = hbt.win;
+    ll.w_L.assign(h_L, h_L + nw);
+    ll.w_nsel.assign(h_nsel, h_nsel + nw);
+    ll.w_nsup.assign(h_nsup, h_nsup + nw);
+    ll.w_rowbase.resize(nw);
+    ll.w_supbase.resize(nw);
+    ll.index.clear();
+    uint64_t rb = 0, sb = 0;
+    for (size_t w = 0; w < nw; w++) {
+        ll.w_rowbase[w] = rb; rb += h_L[w];
+        ll.w_supbase[w] = sb; sb += h_nsup[w];
+        ll.index[((uint64_t)hbt.win[w].rid << 32) | hbt.win[w].wid] = (uint32_t)w;
+    }
+    ll.n_sup = n_sup;
+    ll.total_rows = total_rows;
+    ll.view = b;
+    hbt.clear();
+    return HB_OK;
+}
+
+int append_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
+                  const hb_overlap_window* ow, uint32_t n_ow) {
+    if (!ctx->have_reads) return fail(ctx, HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
+    if (rid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "rid out of range");
+    const uint32_t W = ctx->opt.window_size;
+    const uint32_t len = ctx->read_len[rid];
+    if (n_windows != (len + W - 1) / W) return fail(ctx, HB_ERR_ARG, "n_windows != ceil(read_len / window_size)");
+    if ((n_ovl && !ovl) || (n_ow && !ow)) return fail(ctx, HB_ERR_ARG, "null array");
+    for (uint32_t i = 0; i < n_ovl; i++) {
+        if (ovl[i].tid != rid) return fail(ctx, HB_ERR_ARG, "overlap.tid != rid (alignments must be grouped by target)");
+        if (ovl[i].qid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "overlap.qid out of range");
+        if (!ovl[i].cigar && ovl[i].cigar_len) return fail(ctx, HB_ERR_ARG, "null cigar");
+        if (ovl[i].strand > 1) return fail(ctx, HB_ERR_ARG, "strand must be 0 or 1");
+    }
+    for (uint32_t i = 0; i < n_ow; i++) {
+        if (ow[i].overlap_idx >= n_ovl || ow[i].window_idx >= n_windows) return fail(ctx, HB_ERR_ARG, "overlap_window index out of range");
+        if (ow[i].cigar_end_idx < ow[i].cigar_start_idx || ow[i].cigar_end_idx > ovl[ow[i].overlap_idx].cigar_len)
+            return fail(ctx, HB_ERR_ARG, "overlap_window cigar range out of bounds");
+    }
+    HostBatch& hbt = ctx->hbatch;
+    const uint32_t t_idx = (uint32_t)hbt.tgt.size();
+    const uint32_t ovl_base = (uint32_t)hbt.ovl.size(), win_base = (uint32_t)hbt.win.size(), ow_base = (uint32_t)hbt.ow.size();
+    for (uint32_t i = 0; i < n_ovl; i++) {
+        DevOverlap d{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx};
+        hbt.cig.insert(hbt.cig.end(), ovl[i].cigar, ovl[i].cigar + ovl[i].cigar_len);
+        hbt.ovl.push_back(d);
+    }
+    // bucket the overlap-windows by window, keeping push order (= alignment order) inside each
+    std::vector<uint32_t> cnt(n_windows + 1, 0);
+    for (uint32_t i = 0; i < n_ow; i++) cnt[ow[i].window_idx + 1]++;
+    for (uint32_t w = 0; w < n_windows; w++) cnt[w + 1] += cnt[w];
+    for (uint32_t w = 0; w < n_windows; w++) {
+        DevWin d{};
+        d.tgt = t_idx; d.rid = rid; d.wid = w; d.tstart = w * W;
+        d.len = (w == n_windows - 1) ? len - w * W : W;
+        d.ow_begin = ow_base + cnt[w];
+        d.ow_end = ow_base + cnt[w + 1];
+        hbt.win.push_back(d);
+    }
+    hbt.ow.resize(ow_base + n_ow);
+    std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+    for (uint32_t i = 0; i < n_ow; i++) {
+        const hb_overlap_window& s = ow[i];
+        DevOW d{ovl_base + s.overlap_idx, win_base + s.window_idx, s.tstart, s.qstart, s.qend, s.cigar_start_idx,
+                s.cigar_start_offset, s.cigar_end_idx, s.cigar_end_offset, 0};
+        hbt.ow[ow_base + fill[s.window_idx]++] = d;
+    }
+    for (uint32_t i = 0; i < n_ow; i++) {
+        DevOW& d = hbt.ow[ow_base + i];
+        d.op_base = (uint32_t)hbt.op_cap;
+        hbt.op_cap += (d.cei - d.csi) / 2 + 1;
+    }
+    hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl});
+    if (hbt.tgt.size() >= ctx->opt.launch_targets) return run_batch(ctx);
+    return HB_OK;
+}
+
+}  // namespace
+
+// ========================================================================================
+extern "C" {
+
+const char* hb_last_error(hb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_options* opt) {
+    if (!out || !model_path) { g_create_err = "null argument"; return HB_ERR_ARG; }
+    *out = nullptr;
+    hb_ctx* ctx = new hb_ctx();
+    ctx->device = cuda_device;
+    ctx->opt.struct_size = sizeof(hb_options);
+    ctx->opt.window_size = 4096;
+    ctx->opt.batch_size = 64;
+    ctx->opt.launch_targets = 256;
+    ctx->opt.flags = 0;
+    if (opt) {
+        if (opt->struct_size != sizeof(hb_options)) { g_create_err = "hb_options.struct_size mismatch"; delete ctx; return HB_ERR_ARG; }
+        if (opt->window_size) ctx->opt.window_size = opt->window_size;
+        if (opt->batch_size) ctx->opt.batch_size = opt->batch_size;
+        if (opt->launch_targets) ctx->opt.launch_targets = opt->launch_targets;
+        ctx->opt.flags = opt->flags;
+    }
+    auto bail = [&](int code) { g_create_err = ctx->err; hb_destroy(ctx); return code; };
+    if (ctx->opt.window_size < 8 || ctx->opt.window_size > 8192) { ctx->err = "window_size must be in [8, 8192]"; return bail(HB_ERR_ARG); }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        ctx->err = "no CUDA device: herro_b200 has no CPU fallback";
+        return bail(HB_ERR_CUDA);
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) { ctx->err = "cuda_device out of range"; return bail(HB_ERR_ARG); }
+    if (cudaSetDevice(cuda_device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(HB_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(HB_ERR_CUDA); }
+    for (auto& e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(HB_ERR_CUDA); }
+    if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
+    int rc = load_weights(ctx, model_path);
+    if (rc) return bail(rc);
+    *out = ctx;
+    return HB_OK;
+}
+
+void hb_destroy(hb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->weight_allocs) cudaFree(p);
+    DevBuf* bufs[] = {&ctx->d_words, &ctx->d_word_off, &ctx->d_len, &ctx->d_qual, &ctx->d_qual_off, &ctx->d_ln, &ctx->d_tgt,
+                      &ctx->d_win, &ctx->d_ovl, &ctx->d_ow, &ctx->d_cig, &ctx->d_op_kl, &ctx->d_op_t, &ctx->d_op_q,
+                      &ctx->d_ow_nops, &ctx->d_ow_flags, &ctx->d_ow_acc, &ctx->d_ow_tend, &ctx->d_col_ow, &ctx->d_w_n1,
+                      &ctx->d_w_S, &ctx->d_ovl_n, &ctx->d_ovl_tot, &ctx->d_ovl_score, &ctx->d_sel_ow, &ctx->d_w_nsel,
+                      &ctx->d_rowmap, &ctx->d_w_L, &ctx->d_w_rowbase, &ctx->d_w_nsup, &ctx->d_w_reflmax, &ctx->d_mat_b,
+                      &ctx->d_mat_q, &ctx->d_row_emit, &ctx->d_sup_row, &ctx->d_sup_pk, &ctx->d_w_supbase, &ctx->d_fwd_win,
+                      &ctx->d_fwd_row, &ctx->d_w_outlen, &ctx->d_w_outoff, &ctx->d_out, &ctx->d_tgt_err, &ctx->d_counters,
+                      &ctx->d_ws, &ctx->d_logits, &ctx->d_info};
+    for (DevBuf* b : bufs) b->release();
+    ctx->pin_in.release(); ctx->pin_small.release(); ctx->pin_out.release();
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto& kv : ctx->live) free(kv.second);
+    delete ctx;
+}
+
+int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_words, const uint32_t* seq_len,
+                    const uint8_t* const* qual) {
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!seq_words || !seq_len || !qual || n_reads == 0) return fail(ctx, HB_ERR_ARG, "null/empty read store");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> woff(n_reads + 1, 0), qoff(n_reads + 1, 0);
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        woff[i + 1] = woff[i] + ((uint64_t)seq_len[i] + 31) / 32;
+        qoff[i + 1] = qoff[i] + seq_len[i];
+        max_len = std::max(max_len, seq_len[i]);
+        if (!seq_words[i] || !qual[i]) return fail(ctx, HB_ERR_ARG, "null read");
+    }
+    CK(ctx->d_words.ensure((woff[n_reads] + 1) * 8));
+    CK(ctx->d_qual.ensure(qoff[n_reads] + 16));
+    CK(ctx->d_word_off.ensure((n_reads + 1) * 8));
+    CK(ctx->d_qual_off.ensure((n_reads + 1) * 8));
+    CK(ctx->d_len.ensure((size_t)n_reads * 4));
+    // stage in pinned chunks
+    const size_t CH = 64u << 20;
+    CK(ctx->pin_in.ensure(CH));
+    uint8_t* pin = ctx->pin_in.as<uint8_t>();
+    auto copy_stream = [&](auto getp, auto getn, uint8_t* dbase) -> int {
+        size_t fill = 0, doff = 0;
+        for (uint32_t i = 0; i < n_reads; i++) {
+            const uint8_t* src = (const uint8_t*)getp(i);
+            size_t n = getn(i), so = 0;
+            while (so < n) {
+                const size_t take = std::min(n - so, CH - fill);
+                memcpy(pin + fill, src + so, take);
+                fill += take; so += take;
+                if (fill == CH) {
+                    CK(cudaMemcpy(dbase + doff, pin, fill, cudaMemcpyHostToDevice));
+                    doff += fill; fill = 0;
+                }
+            }
+        }
+        if (fill) CK(cudaMemcpy(dbase + doff, pin, fill, cudaMemcpyHostToDevice));
+        return HB_OK;
+    };
+    int rc = copy_stream([&](uint32_t i) { return (const void*)seq_words[i]; },
+                         [&](uint32_t i) { return (size_t)(((uint64_t)seq_len[i] + 31) / 32 * 8); }, ctx->d_words.as<uint8_t>());
+    if (rc) return rc;
+    rc = copy_stream([&](uint32_t i) { return (const void*)qual[i]; }, [&](uint32_t i) { return (size_t)seq_len[i]; },
+                     ctx->d_qual.as<uint8_t>());
+    if (rc) return rc;
+    CK(cudaMemcpy(ctx->d_word_off.p, woff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_qual_off.p, qoff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_len.p, seq_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
+    // ln(k) table from the host libm — the value Rust's f64::ln returns (src/features.rs:507)
+    ctx->ln_n = max_len + 2;
+    std::vector<double> ln(ctx->ln_n);
+    ln[0] = 0.0;
+    for (uint32_t k = 1; k < ctx->ln_n; k++) ln[k] = std::log((double)k);
+    CK(ctx->d_ln.ensure((size_t)ctx->ln_n * 8));
+    CK(cudaMemcpy(ctx->d_ln.p, ln.data(), (size_t)ctx->ln_n * 8, cudaMemcpyHostToDevice));
+    ctx->stats.h2d_bytes += woff[n_reads] * 8 + qoff[n_reads];
+    ctx->n_reads = n_reads;
+    ctx->read_len.assign(seq_len, seq_len + n_reads);
+    ctx->rs = ReadStoreView{ctx->d_words.as<uint64_t>(), ctx->d_word_off.as<uint64_t>(), ctx->d_len.as<uint32_t>(),
+                            ctx->d_qual.as<uint8_t>(), ctx->d_qual_off.as<uint64_t>(), n_reads};
+    ctx->have_reads = true;
+    return HB_OK;
+}
+
+int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
+                     const hb_overlap_window* ow, uint32_t n_ow) {
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
+    return append_target(ctx, rid, n_windows, ovl, n_ovl, ow, n_ow);
+}
+
+int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->have_reads) return fail(ctx, HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
+    if (rid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "rid out of range");
+    if (n_ovl && !ovl) return fail(ctx, HB_ERR_ARG, "null array");
+    const uint32_t W = ctx->opt.window_size;
+    const uint32_t n_windows = (ctx->read_len[rid] + W - 1) / W;
+    std::vector<hb_overlap_window> ows;  // windowing runs outside the lock: feature threads do it in parallel
+    for (uint32_t i = 0; i < n_ovl; i++) {
+        if (ovl[i].tid != rid) return fail(ctx, HB_ERR_ARG, "overlap.tid != rid");
+        if (host_extract_windows(ovl[i], i, W, n_windows, ows) != 0)
+            return fail(ctx, HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
+    return append_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
+}
+
+int hb_extract_windows(const hb_overlap* ovl, uint32_t overlap_idx, uint32_t window_size, uint32_t n_windows,
+                       hb_overlap_window* out, uint32_t cap, uint32_t* n_out) {
+    if (!ovl || !n_out || window_size == 0) return HB_ERR_ARG;
+    std::vector<hb_overlap_window> v;
+    if (host_extract_windows(*ovl, overlap_idx, window_size, n_windows, v) != 0) return HB_ERR_INPUT;
+    *n_out = (uint32_t)v.size();
+    if (out) memcpy(out, v.data(), std::min<size_t>(v.size(), cap) * sizeof(hb_overlap_window));
+    return HB_OK;
+}
+
+int hb_flush(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
+    return run_batch(ctx);
+}
+
+int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg_len, uint32_t* n_segs) {
+    if (!ctx || !rid || !seqs || !seg_len || !n_segs) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->results.empty()) return 0;
+    Result r = std::move(ctx->results.front());
+    ctx->results.pop_front();
+    const size_t ns = r.seg_len.size();
+    const size_t hdr = (ns * 4 + 15) & ~(size_t)15;
+    uint8_t* blk = (uint8_t*)malloc(hdr + r.seq.size() + 16);
+    if (!blk) return fail(ctx, HB_ERR_CAPACITY, "out of host memory");
+    memcpy(blk, r.seg_len.data(), ns * 4);
+    memcpy(blk + hdr, r.seq.data(), r.seq.size());
+    *rid = r.rid;
+    *seg_len = (uint32_t*)blk;
+    *seqs = blk + hdr;
+    *n_segs = (uint32_t)ns;
+    ctx->live[*seqs] = blk;
+    if (r.status != HB_OK) {
+        ctx->err = "target " + std::to_string(r.rid) + ": input the reference would panic on (malformed CIGAR / window)";
+        return r.status;
+    }
+    return 1;
+}
+
+void hb_release_result(hb_ctx* ctx, uint8_t* seqs) {
+    if (!ctx || !seqs) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->live.find(seqs);
+    if (it != ctx->live.end()) { free(it->second); ctx->live.erase(it); }
+}
+
+int hb_get_stats(hb_ctx* ctx, hb_stats* out) {
+    if (!ctx || !out) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->stats;
+    return HB_OK;
+}
+int hb_reset_stats(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stats = hb_stats{};
+    return HB_OK;
+}
+
+static int find_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* w) {
+    if (!(ctx->opt.flags & HB_FLAG_KEEP_DEBUG)) return fail(ctx, HB_ERR_STATE, "context was not created with HB_FLAG_KEEP_DEBUG");
+    if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch yet");
+    auto it = ctx->last.index.find(((uint64_t)rid << 32) | wid);
+    if (it == ctx->last.index.end()) return fail(ctx, HB_ERR_ARG, "window not part of the most recent launch");
+    *w = it->second;
+    return HB_OK;
+}
+
+int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* shape4) {
+    if (!ctx || !shape4) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    uint32_t w;
+    int rc = find_window(ctx, rid, wid, &w);
+    if (rc) return rc;
+    shape4[0] = ctx->last.w_L[w];
+    shape4[1] = ctx->last.w_nsel[w];
+    shape4[2] = ctx->last.w_nsup[w];
+    shape4[3] = 1;
+    return HB_OK;
+}
+
+int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases, uint8_t* quals, uint32_t* supported,
+                         uint32_t* sup_rows, float* info_logits, float* bases_logits) {
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    uint32_t w;
+    int rc = find_window(ctx, rid, wid, &w);
+    if (rc) return rc;
+    const LastLaunch& ll = ctx->last;
+    const uint32_t L = ll.w_L[w], ns = ll.w_nsup[w];
+    const uint64_t rb = ll.w_rowbase[w], sb = ll.w_supbase[w];
+    std::vector<uint8_t> tmp((size_t)L * ROW_BYTES);
+    for (int pass = 0; pass < 2; pass++) {
+        uint8_t* dst = pass ? quals : bases;
+        if (!dst || !L) continue;
+        CK(cudaMemcpy(tmp.data(), (pass ? ll.view.mat_quals : ll.view.mat_bases) + rb * ROW_BYTES, tmp.size(), cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < L; r++) memcpy(dst + (size_t)r * R_COLS, tmp.data() + (size_t)r * ROW_BYTES, R_COLS);
+    }
+    if (ns) {
+        std::vector<uint32_t> t(ns);
+        if (supported) {
+            CK(cudaMemcpy(t.data(), ll.view.sup_pk + rb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+            for (uint32_t k = 0; k < ns; k++) { supported[2 * k] = (t[k] >> 8) & 0xffffu; supported[2 * k + 1] = t[k] & 0xffu; }
+        }
+        if (sup_rows) CK(cudaMemcpy(sup_rows, ll.view.sup_row + rb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+        if (info_logits) CK(cudaMemcpy(info_logits, ctx->d_info.as<float>() + sb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+        if (bases_logits) CK(cudaMemcpy(bases_logits, ctx->d_logits.as<float>() + sb * 5, (size_t)ns * 20, cudaMemcpyDeviceToHost));
+    }
+    return HB_OK;
+}
+
+int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {
+    if (!ctx || !ms) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch to replay");
+    const BatchView b = ctx->last.view;
+    uint64_t launches = 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    for (uint32_t it = 0; it < iters; it++) {
+        int rc = zero_scratch(ctx, b);
+        if (rc) return rc;
+        launches += launch_features_a(b, ctx->stream);
+        launches += launch_pileup(b, ctx->stream);
+        launches += launch_features_c1(b, ctx->stream);
+        rc = launch_tail(ctx, b, ctx->last.n_sup, &launches);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
+    ctx->stats.kernel_launches += launches;
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,733 @@
+// features.cu — sm_100a kernels for the pileup ("features") and consensus stages.
+//
+// Reference semantics: src/features.rs:44-722 (extract_features and helpers),
+// src/inference.rs:214-268 (token map, target indices), src/consensus.rs:86-227.
+// The structure is NOT the reference's: the reference materialises a first-pass
+// [L, 1+max(n,30)] matrix per window only to (a) find first-pass supported rows and
+// (b) count per-read matches on them, then re-stacks 31 columns and drops all-gap rows.
+// Here:
+//   pass 1  works position-major without insertion rows (only base rows feed the ranking,
+//           src/features.rs:481-491) and never writes a matrix;
+//   pass 2  builds the final [L',31] matrix directly: dropping all-gap rows of the
+//           re-stacked matrix (src/features.rs:531-556) is the same as recomputing max_ins
+//           over the 31 selected columns only;
+//   the second get_supported (src/features.rs:558) and the non-supported branch of
+//   consensus (src/consensus.rs:176-217, the majority vote) are evaluated on the tile while
+//   it is still in shared memory.
+#include "common.cuh"
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------
+// K1: tokenise the CIGAR slice of every overlap-window, clip it (App. A.3), prefix-sum the
+//     target/query offsets, apply the indel filter and compute calculate_accuracy.
+//     One warp per overlap-window.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= b.n_ow) return;
+    const DevOW ow = b.ow[wi];
+    const DevOverlap ov = b.ovl[ow.ovl];
+    const DevWin win = b.win[ow.win];
+    const uint8_t* __restrict__ cg = b.cig + ov.cig_off + ow.csi;
+    const int slen = (int)ow.cei - (int)ow.csi;
+    uint32_t flags = 0;
+    if (slen <= 0 || ow.cei > ov.cig_len) flags |= OWF_BAD;
+    if (ow.tstart < win.tstart || ow.tstart >= win.tstart + win.len) flags |= OWF_BAD;
+    // query region must lie inside the query read (decode() asserts, src/haec_io.rs:157)
+    {
+        uint32_t qlen = b.rs.len[ov.qid];
+        if (ow.qend < ow.qstart) flags |= OWF_BAD;
+        if (!ov.strand) {
+            if ((uint64_t)ov.qstart + ow.qend > qlen) flags |= OWF_BAD;
+        } else {
+            if (ov.qend < ow.qend || ov.qend - ow.qstart > qlen) flags |= OWF_BAD;
+        }
+    }
+    uint32_t nops = 0;
+    if (!(flags & OWF_BAD)) {
+        // ---- parse: lanes 0..9 look back, lanes 10..31 are the 22 active bytes of this step
+        for (int base = 0; base < slen; base += 22) {
+            const int idx = base - 10 + lane;
+            const bool inrange = idx >= 0 && idx < slen;
+            const int c = inrange ? (int)__ldg(cg + idx) : 0;
+            const bool active = lane >= 10 && inrange;
+            const bool is_digit = inrange && c >= '0' && c <= '9';
+            const bool is_letter = active && !is_digit;
+            uint32_t num = 0, mul = 1;
+            bool stop = false;
+            int ndig = 0;
+#pragma unroll
+            for (int s = 1; s <= 10; s++) {
+                const int pc = __shfl_up_sync(HB_FULL, c, s);
+                const bool pd = __shfl_up_sync(HB_FULL, (int)is_digit, s) != 0;
+                const bool ok = (lane >= s) && pd;
+                if (!stop && ok) {
+                    num += (uint32_t)(pc - '0') * mul;
+                    mul *= 10u;
+                    ndig++;
+                } else {
+                    stop = true;
+                }
+            }
+            const uint32_t mask = __ballot_sync(HB_FULL, is_letter);
+            if (is_letter) {
+                uint32_t kind = (c == 'M') ? OP_M : (c == 'I') ? OP_I : (c == 'D') ? OP_D : 1u;
+                // 10 digits could overflow u32 and a longer number would be truncated: both are
+                // outside anything an aligner emits; flag them like the other parse errors.
+                if (kind == 1u || num == 0 || ndig == 0 || ndig >= 10) flags |= OWF_BAD;
+                const uint32_t k = nops + __popc(mask & ((1u << lane) - 1u));
+                b.op_kl[ow.op_base + k] = kind | (num << 2);
+            }
+            nops += __popc(mask);
+        }
+        // the slice must end on an op letter (CigarIter would index past the end otherwise)
+        if (lane == 0) {
+            int lc = __ldg(cg + slen - 1);
+            if (lc >= '0' && lc <= '9') flags |= OWF_BAD;
+        }
+        flags = __reduce_or_sync(HB_FULL, flags);
+        if (nops == 0) flags |= OWF_BAD;
+    }
+    __syncwarp();
+
+    uint32_t tcur = ow.tstart - win.tstart, qcur = 0;
+    uint32_t sum_i = 0, sum_d = 0, sum_m = 0;
+    if (!(flags & OWF_BAD)) {
+        // ---- clip (first / last / single op) and prefix-sum offsets
+        for (uint32_t k0 = 0; k0 < nops; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint32_t kind = 0, raw = 0, eff = 0;
+            if (k < nops) {
+                const uint32_t kl = b.op_kl[ow.op_base + k];
+                kind = kl & 3u;
+                raw = kl >> 2;
+                eff = raw;
+                if (nops == 1) {
+                    if (ow.ceo <= ow.cso) flags |= OWF_BAD;  // assert, src/features.rs:592-597
+                    eff = ow.ceo - ow.cso;
+                } else if (k == 0) {
+                    if (raw <= ow.cso) flags |= OWF_BAD;  // assert, src/features.rs:600-608
+                    eff = raw - ow.cso;
+                } else if (k == nops - 1) {
+                    eff = ow.ceo;
+                }
+                if (eff == 0) flags |= OWF_BAD;  // "Operation length cannot be 0"
+                if ((kind == OP_I || kind == OP_D) && raw > 50) flags |= OWF_LONG_INDEL;  // unclipped (H2)
+                // get_max_ins uses the unclipped insertion length (H3); with windows produced by
+                // extract_windows an insertion is never clipped and never first.
+                if (kind == OP_I && (eff != raw || k == 0)) flags |= OWF_BAD;
+            }
+            const uint32_t dt = (k < nops && kind != OP_I) ? eff : 0;
+            const uint32_t dq = (k < nops && kind != OP_D) ? eff : 0;
+            const uint32_t it = warp_incl_scan(dt, lane), iq = warp_incl_scan(dq, lane);
+            if (k < nops) {
+                b.op_kl[ow.op_base + k] = kind | (eff << 2);
+                b.op_t[ow.op_base + k] = tcur + it - dt;
+                b.op_q[ow.op_base + k] = qcur + iq - dq;
+            }
+            sum_i += (k < nops && kind == OP_I) ? eff : 0;
+            sum_d += (k < nops && kind == OP_D) ? eff : 0;
+            sum_m += (k < nops && kind == OP_M) ? eff : 0;
+            tcur += __shfl_sync(HB_FULL, it, 31);
+            qcur += __shfl_sync(HB_FULL, iq, 31);
+        }
+        flags = __reduce_or_sync(HB_FULL, flags);
+        sum_i = warp_sum(sum_i);
+        sum_d = warp_sum(sum_d);
+        sum_m = warp_sum(sum_m);
+        if (tcur > win.len) flags |= OWF_BAD;                    // writes past the window
+        if (qcur != ow.qend - ow.qstart) flags |= OWF_BAD;       // query_iter would run dry / leave bases
+    }
+    __syncwarp();
+
+    float acc = 0.f;
+    if (!(flags & (OWF_BAD | OWF_LONG_INDEL))) {
+        // ---- calculate_accuracy (src/features.rs:585-679): matches over M ops
+        const QView qv = make_qview(b.rs, ov, ow);
+        const uint64_t* __restrict__ tw = b.rs.words + b.rs.word_off[win.rid];
+        uint32_t m = 0;
+        for (uint32_t k = 0; k < nops; k++) {
+            const uint32_t kl = b.op_kl[ow.op_base + k];
+            if ((kl & 3u) != OP_M) continue;
+            const uint32_t eff = kl >> 2, t0 = win.tstart + b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
+            for (uint32_t j = lane; j < eff; j += 32) m += (code_at(tw, t0 + j) == qv.code(q0 + j)) ? 1u : 0u;
+        }
+        m = warp_sum(m);
+        const uint32_t tot = sum_m + sum_i + sum_d;  // m + s + i + d
+        acc = __fdiv_rn((float)m, (float)tot);       // src/features.rs:678
+    }
+    if (lane == 0) {
+        b.ow_nops[wi] = nops;
+        b.ow_flags[wi] = flags;
+        b.ow_acc[wi] = acc;
+        b.ow_tend[wi] = tcur;
+        if (flags & OWF_BAD) atomicOr(&b.tgt_err[win.tgt], TERR_BAD_INPUT);
+    }
+}
+
+// Walk the (clipped) ops of one overlap-window with a whole warp.  fm(p, x) is called for
+// every matched base (window-relative target position p, oriented query offset x), fd(p)
+// for every deleted target position; lanes stride over the bases of an op.
+template <class FM, class FD>
+__device__ __forceinline__ void walk_md(const BatchView& b, uint32_t opb, uint32_t nops, int lane, FM fm, FD fd) {
+    for (uint32_t k = 0; k < nops; k++) {
+        const uint32_t kl = b.op_kl[opb + k];
+        const uint32_t kind = kl & 3u, eff = kl >> 2;
+        if (kind == OP_I) continue;
+        const uint32_t t0 = b.op_t[opb + k];
+        if (kind == OP_M) {
+            const uint32_t q0 = b.op_q[opb + k];
+            for (uint32_t j = lane; j < eff; j += 32) fm(t0 + j, q0 + j);
+        } else {
+            for (uint32_t j = lane; j < eff; j += 32) fd(t0 + j);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2: first pass of one window.  filter + stable sort by -accuracy (src/features.rs:376-409),
+//     first-pass supported base rows (get_supported on the [L, 1+max(n,30)] matrix, :438,
+//     restricted to base rows because only those enter the ranking, :481-491) and per-column
+//     match counts on them (:461-500).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pass1(BatchView b) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t W = b.W;
+    uint32_t* cnt_ac = (uint32_t*)smem_raw;
+    uint32_t* cnt_gt = cnt_ac + W;
+    uint32_t* cnt_gp = cnt_gt + W;
+    uint32_t* supbits = cnt_gp + W;                   // (W+31)/32 words
+    float* key = (float*)(supbits + ((W + 31) >> 5));  // MAX_COLS
+    uint32_t* cand = (uint32_t*)(key + MAX_COLS);      // MAX_COLS
+    __shared__ uint32_t s_n1, s_S, s_warp[8];
+
+    const uint32_t w = blockIdx.x;
+    const DevWin win = b.win[w];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_in = win.ow_end - win.ow_begin;
+    if (tid == 0) { s_n1 = 0; s_S = 0; }
+    __syncthreads();
+    if (n_in > MAX_COLS) {
+        if (tid == 0) { atomicOr(&b.tgt_err[win.tgt], TERR_TOO_MANY_COLS); b.w_n1[w] = 0; b.w_S[w] = 0; }
+        return;
+    }
+    // ---- filter (order preserving compaction; n_in <= MAX_COLS so <= 4 rounds)
+    for (uint32_t base = 0; base < n_in; base += 256) {
+        const uint32_t i = base + tid;
+        const bool keep = i < n_in && !(b.ow_flags[win.ow_begin + i] & (OWF_LONG_INDEL | OWF_BAD));
+        const uint32_t m = __ballot_sync(HB_FULL, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t off = s_n1;
+        for (int k = 0; k < warp; k++) off += s_warp[k];
+        if (keep) {
+            const uint32_t pos = off + __popc(m & ((1u << lane) - 1u));
+            cand[pos] = win.ow_begin + i;
+            key[pos] = -b.ow_acc[win.ow_begin + i];  // OrderedFloat(-acc)
+        }
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_n1 += t; }
+        __syncthreads();
+    }
+    const uint32_t n1 = s_n1;
+    // ---- stable ascending sort on key by rank counting
+    for (uint32_t i = tid; i < n1; i += 256) {
+        const float ki = key[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n1; j++) {
+            const float kj = key[j];
+            r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
+        }
+        b.col_ow[win.ow_begin + r] = cand[i];
+    }
+    for (uint32_t p = tid; p < W; p += 256) { cnt_ac[p] = 0; cnt_gt[p] = 0; cnt_gp[p] = 0; }
+    __syncthreads();  // also makes col_ow (global, written by this block) visible below
+
+    // ---- allele counts per target position over all columns
+    const uint64_t* __restrict__ tw = b.rs.words + b.rs.word_off[win.rid];
+    for (uint32_t c = warp; c < n1; c += 8) {
+        const uint32_t owi = cand[c];  // order is irrelevant for counting
+        const DevOW ow = b.ow[owi];
+        const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+        walk_md(b, ow.op_base, b.ow_nops[owi], lane,
+                [&](uint32_t p, uint32_t x) {
+                    const uint32_t cd = qv.code(x);
+                    atomicAdd((cd & 2u) ? &cnt_gt[p] : &cnt_ac[p], (cd & 1u) ? 0x10000u : 1u);
+                },
+                [&](uint32_t p) { atomicAdd(&cnt_gp[p], 1u); });
+    }
+    __syncthreads();
+    // ---- threshold: floor(0.1 * ncols) in f64 (src/features.rs:712), >= 2 alleles (:713-718)
+    const uint32_t ncols = 1u + (n1 > (uint32_t)TOP_K ? n1 : (uint32_t)TOP_K);
+    const uint32_t thresh = (uint32_t)((double)ncols * 0.1);
+    uint32_t S_local = 0;
+    for (uint32_t p0 = warp * 32; p0 < W; p0 += 256) {
+        const uint32_t p = p0 + lane;
+        bool sup = false;
+        if (p < win.len) {
+            uint32_t a = cnt_ac[p] & 0xffffu, c = cnt_ac[p] >> 16, g = cnt_gt[p] & 0xffffu, t = cnt_gt[p] >> 16;
+            const uint32_t gp = cnt_gp[p];
+            const uint32_t tc = code_at(tw, win.tstart + p);  // the target column's own base
+            a += (tc == 0); c += (tc == 1); g += (tc == 2); t += (tc == 3);
+            const uint32_t ns = (a >= thresh) + (c >= thresh) + (g >= thresh) + (t >= thresh) + (gp >= thresh);
+            sup = ns >= 2;
+        }
+        const uint32_t m = __ballot_sync(HB_FULL, sup);
+        if (lane == 0) { supbits[p0 >> 5] = m; S_local += __popc(m); }
+    }
+    if (lane == 0 && S_local) atomicAdd(&s_S, S_local);
+    __syncthreads();
+    const uint32_t S = s_S;
+    // ---- per-column matches on supported base rows; '.'/gap cells count as mismatches (H1),
+    //      hence d = S - n for every column of the window.
+    if (S > 0) {
+        for (uint32_t c = warp; c < n1; c += 8) {
+            const uint32_t owi = cand[c];
+            const DevOW ow = b.ow[owi];
+            const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+            uint32_t n = 0;
+            walk_md(b, ow.op_base, b.ow_nops[owi], lane,
+                    [&](uint32_t p, uint32_t x) {
+                        if ((supbits[p >> 5] >> (p & 31)) & 1u) n += (qv.code(x) == code_at(tw, win.tstart + p)) ? 1u : 0u;
+                    },
+                    [&](uint32_t) {});
+            n = warp_sum(n);
+            if (lane == 0) {
+                atomicAdd(&b.ovl_n[ow.ovl], n);
+                atomicAdd(&b.ovl_tot[ow.ovl], S);
+            }
+        }
+    }
+    if (tid == 0) { b.w_n1[w] = n1; b.w_S[w] = S; }
+}
+
+// K3: score = n/(n+d) * ln(n+d+1) in f64 (src/features.rs:505-507); ln from the host-libm table so
+//     that it is the value Rust's f64::ln (glibc log) produces.
+__global__ void k_scores(BatchView b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_ovl) return;
+    const uint32_t n = b.ovl_n[i], tot = b.ovl_tot[i];
+    double s = 0.0;
+    if (tot > 0) {
+        const double nd = (double)n, td = (double)tot;
+        const uint32_t k = tot + 1u;
+        const double l = (k < b.ln_table_n) ? b.ln_table[k] : log((double)k);
+        s = __dmul_rn(__ddiv_rn(nd, td), l);
+    }
+    b.ovl_score[i] = s;
+}
+
+// ------------------------------------------------------------------------------------
+// K4: second ranking (stable, descending score; src/features.rs:503-513), top-30 selection,
+//     max_ins over the selected columns, row map row'(p) and L'.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pass2a(BatchView b) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t W = b.W;
+    uint32_t* mi = (uint32_t*)smem_raw;            // W + 1
+    double* sc = (double*)(mi + ((W + 2) & ~1u));   // MAX_COLS
+    __shared__ uint32_t s_sel[TOP_K], s_warp[8], s_carry;
+
+    const uint32_t w = blockIdx.x;
+    const DevWin win = b.win[w];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n1 = b.w_n1[w];
+    const uint32_t nsel = n1 < (uint32_t)TOP_K ? n1 : (uint32_t)TOP_K;
+    for (uint32_t i = tid; i < n1; i += 256) sc[i] = b.ovl_score[b.ow[b.col_ow[win.ow_begin + i]].ovl];
+    for (uint32_t p = tid; p <= W; p += 256) mi[p] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n1; i += 256) {
+        const double si = sc[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n1; j++) {
+            const double sj = sc[j];
+            r += (sj > si || (sj == si && j < i)) ? 1u : 0u;
+        }
+        if (r < (uint32_t)TOP_K) {
+            s_sel[r] = b.col_ow[win.ow_begin + i];
+            b.sel_ow[w * TOP_K + r] = s_sel[r];
+        }
+    }
+    __syncthreads();
+    // max_ins over selected columns (src/features.rs:44-95 restricted to the kept columns)
+    for (uint32_t c = warp; c < nsel; c += 8) {
+        const uint32_t owi = s_sel[c];
+        const uint32_t opb = b.ow[owi].op_base, nops = b.ow_nops[owi];
+        for (uint32_t k = lane; k < nops; k += 32) {
+            const uint32_t kl = b.op_kl[opb + k];
+            if ((kl & 3u) == OP_I) {
+                const uint32_t tp = b.op_t[opb + k];  // >= 1 (an insertion is never the first op)
+                atomicMax(&mi[tp - 1], kl >> 2);
+            }
+        }
+    }
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    // exclusive scan of (1 + max_ins[p]) -> row'(p)   (App. A.5)
+    uint32_t* rm = b.rowmap + (size_t)w * (W + 1);
+    for (uint32_t base = 0; base < win.len; base += 256) {
+        const uint32_t p = base + tid;
+        const uint32_t v = p < win.len ? 1u + mi[p] : 0u;
+        const uint32_t inc = warp_incl_scan(v, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t off = s_carry;
+        for (int k = 0; k < warp; k++) off += s_warp[k];
+        if (p < win.len) rm[p] = off + inc - v;
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_carry += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        rm[win.len] = s_carry;
+        b.w_L[w] = s_carry;
+        b.w_nsel[w] = nsel;
+    }
+}
+
+// K5: exclusive scan of a u32 array into u64 offsets with one block (n up to a few 100k).
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                   uint32_t n, uint32_t* counters, int total_slot, uint64_t cap,
+                                                   int overflow_slot) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < n ? in[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(HB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint64_t off = s_carry;
+        for (int k = 0; k < warp; k++) off += s_warp[k];
+        if (i < n) out[i] = off + inc - v;
+        __syncthreads();
+        if (tid == 0) { uint64_t t = 0; for (int k = 0; k < 32; k++) t += s_warp[k]; s_carry += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counters[total_slot] = (uint32_t)(s_carry & 0xffffffffu);
+        counters[total_slot + 1] = (uint32_t)(s_carry >> 32);
+        if (overflow_slot >= 0 && s_carry > cap) counters[overflow_slot] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K7: build the final [L',31] token/quality matrix of one window tile by tile in shared
+//     memory, evaluate the second get_supported (thresh = floor(3.1) = 3) and the majority vote
+//     on the tile, and stream the tile to HBM with 16-byte stores.          (the pileup kernel)
+// ------------------------------------------------------------------------------------
+constexpr int TR = 512;  // rows per tile
+
+__global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
+    __shared__ __align__(16) uint8_t t_tok[TR * ROW_BYTES];
+    __shared__ __align__(16) uint8_t t_q[TR * ROW_BYTES];
+    __shared__ uint32_t rm_s[TR + 2];
+    __shared__ uint32_t pk_s[TR];
+    __shared__ uint8_t sup_s[TR];
+    __shared__ uint32_t c_ow[32], c_rs[32], c_re[32], c_gap[32];
+    __shared__ uint32_t s_phi, s_warp[8], s_nsup;
+
+    const uint32_t w = blockIdx.x;
+    const DevWin win = b.win[w];
+    const uint32_t W = b.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nsel = b.w_nsel[w];
+    const uint32_t L = b.w_L[w];
+    const uint64_t rowbase = b.w_rowbase[w];
+    if (b.counters[CNT_OVERFLOW]) return;  // arena too small: host grows it and re-launches
+    const uint32_t* __restrict__ rm = b.rowmap + (size_t)w * (W + 1);
+    const uint64_t* __restrict__ tw = b.rs.words + b.rs.word_off[win.rid];
+    const uint8_t* __restrict__ tq = b.rs.qual + b.rs.qual_off[win.rid] + win.tstart;
+
+    if (tid < 32) {
+        uint32_t owi = 0, rs = 0, re = 0, gap = TOK_NONE;
+        if (tid >= 1 && (uint32_t)tid <= nsel) {
+            owi = b.sel_ow[w * TOP_K + tid - 1];
+            const DevOW ow = b.ow[owi];
+            rs = rm[ow.tstart - win.tstart];       // rows before are '.' (src/features.rs:166-171)
+            re = rm[b.ow_tend[owi]];               // rows from here on are '.' (:233-236)
+            gap = b.ovl[ow.ovl].strand ? TOK_GAP_R : TOK_GAP_F;
+        } else if (tid == 0) {
+            rs = 0; re = L; gap = TOK_GAP_F;       // target column: bases.fill('*') (:248)
+        }
+        c_ow[tid] = owi; c_rs[tid] = rs; c_re[tid] = re; c_gap[tid] = gap;
+    }
+    if (tid == 0) s_nsup = 0;
+
+    // per-warp op cursors for the (up to 4) columns this warp owns: columns warp+1, warp+9, ...
+    uint32_t cur[4] = {0, 0, 0, 0};
+    uint32_t p_lo = 0;
+    __syncthreads();
+
+    for (uint32_t r0 = 0; r0 < L; r0 += TR) {
+        const uint32_t r1 = min(r0 + (uint32_t)TR, L);
+        // ---- positions touching this tile: p_lo .. p_hi-1 ; rm_s[i] = row'(p_lo + i)
+        for (uint32_t i = tid; i < TR + 2; i += 256) {
+            const uint32_t p = p_lo + i;
+            rm_s[i] = p <= win.len ? rm[p] : 0xffffffffu;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < TR + 1; i += 256) {
+            // first p with row'(p) >= r1
+            if (rm_s[i] >= r1 && (i == 0 || rm_s[i - 1] < r1)) s_phi = p_lo + i;
+        }
+        // ---- initial fill: gap inside a column's aligned row range, '.' outside, '!' quals
+        for (uint32_t rr = warp; rr < (uint32_t)TR; rr += 8) {
+            const uint32_t row = r0 + rr;
+            uint32_t tok = TOK_NONE;
+            if (row >= c_rs[lane] && row < c_re[lane]) tok = c_gap[lane];
+            t_tok[rr * ROW_BYTES + lane] = (uint8_t)tok;
+            t_q[rr * ROW_BYTES + lane] = QUAL_EMPTY;
+        }
+        __syncthreads();
+        const uint32_t p_hi = s_phi;
+        // ---- target column + (pos, ins) of every row
+        for (uint32_t p = p_lo + tid; p < p_hi; p += 256) {
+            const uint32_t row = rm_s[p - p_lo], nxt = rm_s[p - p_lo + 1];
+            if (row >= r0) {
+                t_tok[(row - r0) * ROW_BYTES] = (uint8_t)code_at(tw, win.tstart + p);
+                t_q[(row - r0) * ROW_BYTES] = __ldg(tq + p);
+            }
+            for (uint32_t k = 0; row + k < nxt; k++) {
+                const uint32_t r = row + k;
+                if (r >= r0 && r < r1) pk_s[r - r0] = (p << 8) | (k & 0xffu);
+            }
+        }
+        // ---- overlap columns: scatter matched and inserted bases
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t c = 1 + warp + 8 * s;
+            if (c > nsel) continue;
+            const uint32_t owi = c_ow[c];
+            const DevOW ow = b.ow[owi];
+            const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+            const uint32_t nops = b.ow_nops[owi];
+            const uint32_t add = qv.rev ? 5u : 0u;
+            uint32_t k = cur[s];
+            bool advancing = true;
+            for (; k < nops; k++) {
+                const uint32_t kl = b.op_kl[ow.op_base + k];
+                const uint32_t kind = kl & 3u, eff = kl >> 2;
+                const uint32_t t0 = b.op_t[ow.op_base + k];
+                if (t0 > p_hi) break;
+                if (kind == OP_I) {
+                    const uint32_t pp = t0 - 1;  // insertion after target position pp
+                    if (pp >= p_lo && pp < p_hi) {
+                        const uint32_t q0 = b.op_q[ow.op_base + k];
+                        const uint32_t rb = rm_s[pp - p_lo] + 1;
+                        for (uint32_t j = lane; j < eff; j += 32) {
+                            const uint32_t r = rb + j;
+                            if (r >= r0 && r < r1) {
+                                t_tok[(r - r0) * ROW_BYTES + c] = (uint8_t)(qv.code(q0 + j) + add);
+                                t_q[(r - r0) * ROW_BYTES + c] = qv.q(q0 + j);
+                            }
+                        }
+                    }
+                    // done for later tiles iff its slots lie before position p_hi-1
+                    if (advancing && t0 < p_hi) cur[s] = k + 1; else advancing = false;
+                } else {
+                    const uint32_t lo = max(t0, p_lo), hi = min(t0 + eff, p_hi);
+                    if (kind == OP_M && lo < hi) {
+                        const uint32_t q0 = b.op_q[ow.op_base + k];
+                        for (uint32_t p = lo + lane; p < hi; p += 32) {
+                            const uint32_t r = rm_s[p - p_lo];
+                            if (r >= r0) {
+                                t_tok[(r - r0) * ROW_BYTES + c] = (uint8_t)(qv.code(q0 + (p - t0)) + add);
+                                t_q[(r - r0) * ROW_BYTES + c] = qv.q(q0 + (p - t0));
+                            }
+                        }
+                    }
+                    if (advancing && t0 + eff < p_hi) cur[s] = k + 1; else advancing = false;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- per-row: second get_supported (src/features.rs:681-722 on [L',31]) and the
+        //      majority vote of consensus (src/consensus.rs:176-200).  warp per row, lane = column.
+        for (uint32_t rr = warp; rr < r1 - r0; rr += 8) {
+            const uint32_t tok = t_tok[rr * ROW_BYTES + lane];
+            const bool live = lane < R_COLS && tok < TOK_NONE;
+            const uint32_t cls = tok >= 5 ? tok - 5 : tok;  // BASES_UPPER_COUNTER / BASE_FORWARD
+            uint32_t cnt[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) cnt[k] = __popc(__ballot_sync(HB_FULL, live && cls == (uint32_t)k));
+            if (lane == 0) {
+                const uint32_t ns = (cnt[0] >= 3) + (cnt[1] >= 3) + (cnt[2] >= 3) + (cnt[3] >= 3) + (cnt[4] >= 3);
+                const bool sup = ns >= 2;
+                // two most common, stable on ties (A<C<G<T<*)
+                uint32_t b0 = 0;
+#pragma unroll
+                for (int k = 1; k < 5; k++) if (cnt[k] > cnt[b0]) b0 = k;
+                uint32_t b1 = b0 == 0 ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) if ((uint32_t)k != b0 && (uint32_t)k != b1 && cnt[k] > cnt[b1]) b1 = k;
+                // (the loop above keeps the lowest index among equal counts because it only
+                //  replaces on strictly greater and starts from the lowest candidate)
+                const uint32_t tb = cls;  // lane 0 = target column, token 0..4
+                const uint32_t base = (cnt[b0] < 2 || (cnt[b0] == cnt[b1] && (b0 == tb || b1 == tb))) ? tb : b0;
+                const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
+                b.row_emit[rowbase + r0 + rr] = (uint8_t)(emit | (sup ? 0x80u : 0u));
+                sup_s[rr] = sup ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        // ---- ordered list of supported rows
+        for (uint32_t base = 0; base < r1 - r0; base += 256) {
+            const uint32_t rr = base + tid;
+            const bool f = rr < r1 - r0 && sup_s[rr];
+            const uint32_t m = __ballot_sync(HB_FULL, f);
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            uint32_t off = s_nsup;
+            for (int k = 0; k < warp; k++) off += s_warp[k];
+            if (f) {
+                const uint32_t pos = off + __popc(m & ((1u << lane) - 1u));
+                b.sup_row[rowbase + pos] = r0 + rr;
+                b.sup_pk[rowbase + pos] = pk_s[rr];
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_nsup += t; }
+            __syncthreads();
+        }
+        // ---- stream the tile out (32 B per row, 16-byte stores)
+        {
+            const uint32_t n16 = (r1 - r0) * 2;
+            uint4* gb = (uint4*)(b.mat_bases + (rowbase + r0) * ROW_BYTES);
+            uint4* gq = (uint4*)(b.mat_quals + (rowbase + r0) * ROW_BYTES);
+            const uint4* sb = (const uint4*)t_tok;
+            const uint4* sq = (const uint4*)t_q;
+            for (uint32_t i = tid; i < n16; i += 256) { gb[i] = sb[i]; gq[i] = sq[i]; }
+        }
+        // next tile starts at the position whose rows straddle r1
+        p_lo = (p_hi <= win.len && p_hi > 0 && rm_s[p_hi - p_lo] == r1) ? p_hi : p_hi - 1;
+        __syncthreads();
+    }
+    if (tid == 0) b.w_nsup[w] = s_nsup;
+}
+
+// K6: Lmax of the reference's collate batch (src/inference.rs:73-84) for each window: the
+//     reference flushes after `-b` consecutive windows of a read and at the end of the read
+//     (src/features.rs:884-893); the windows with >= 1 supported row of such a group form one
+//     batch tensor padded to the longest of them.
+__global__ void k_ref_lmax(BatchView b) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.n_tgt) return;
+    const DevTarget tg = b.tgt[t];
+    for (uint32_t g0 = tg.win_begin; g0 < tg.win_end; g0 += b.batch_size) {
+        const uint32_t g1 = min(g0 + b.batch_size, tg.win_end);
+        uint32_t lmax = 0;
+        for (uint32_t w = g0; w < g1; w++) if (b.w_nsup[w] > 0) lmax = max(lmax, b.w_L[w]);
+        for (uint32_t w = g0; w < g1; w++) b.w_reflmax[w] = lmax;
+    }
+}
+
+// K8: flatten the per-window supported lists into the forward work list.
+__global__ void __launch_bounds__(256) k_fwd_list(BatchView b) {
+    const uint32_t w = blockIdx.x;
+    const uint32_t n = b.w_nsup[w];
+    const uint64_t src = b.w_rowbase[w], dst = b.w_supbase[w];
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        b.fwd_win[dst + i] = w;
+        b.fwd_row[dst + i] = b.sup_row[src + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Consensus: count / write the emitted bases of every window (src/consensus.rs:103-224).
+// row_emit already holds the majority-vote base of every row and, for supported rows, the
+// argmax class written by the forward head (H9).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cons_count(BatchView b) {
+    __shared__ uint32_t s_tot;
+    const uint32_t w = blockIdx.x;
+    if (threadIdx.x == 0) s_tot = 0;
+    __syncthreads();
+    const uint32_t L = b.w_L[w];
+    const uint8_t* e = b.row_emit + b.w_rowbase[w];
+    uint32_t c = 0;
+    if (b.w_nsel[w] >= 2)
+        for (uint32_t r = threadIdx.x; r < L; r += 256) c += ((e[r] & 7u) != 4u) ? 1u : 0u;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) b.w_outlen[w] = s_tot;
+}
+
+__global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
+    __shared__ uint32_t s_warp[8], s_carry;
+    const uint32_t w = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b.w_outlen[w] == 0) return;
+    const uint32_t L = b.w_L[w];
+    const uint8_t* e = b.row_emit + b.w_rowbase[w];
+    uint8_t* out = b.out_bytes + b.w_outoff[w];
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < L; base += 256) {
+        const uint32_t r = base + tid;
+        const uint32_t cls = r < L ? (e[r] & 7u) : 4u;
+        const bool f = cls != 4u;
+        const uint32_t m = __ballot_sync(HB_FULL, f);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t off = s_carry;
+        for (int k = 0; k < warp; k++) off += s_warp[k];
+        if (f) out[off + __popc(m & ((1u << lane) - 1u))] = "ACGT"[cls];
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_carry += t; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// launch wrappers (called from ctx.cu)
+// ------------------------------------------------------------------------------------
+size_t pass1_smem(uint32_t W) { return (size_t)W * 12 + ((W + 31) / 32) * 4 + MAX_COLS * 8 + 64; }
+size_t pass2a_smem(uint32_t W) { return (size_t)((W + 2) & ~1u) * 4 + MAX_COLS * 8 + 64; }
+
+cudaError_t features_configure(uint32_t W) {
+    cudaError_t e = cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass1_smem(W));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pass2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2a_smem(W));
+}
+
+int launch_features_a(const BatchView& b, cudaStream_t st) {
+    int n = 0;
+    if (b.n_ow) { k_tokenize<<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); n++; }
+    k_pass1<<<b.n_win, 256, pass1_smem(b.W), st>>>(b); n++;
+    if (b.n_ovl) { k_scores<<<(b.n_ovl + 255) / 256, 256, 0, st>>>(b); n++; }
+    k_pass2a<<<b.n_win, 256, pass2a_smem(b.W), st>>>(b); n++;
+    k_scan_u32<<<1, 1024, 0, st>>>(b.w_L, b.w_rowbase, b.n_win, b.counters, CNT_TOTAL_ROWS, b.rows_cap, CNT_OVERFLOW); n++;
+    return n;
+}
+int launch_pileup(const BatchView& b, cudaStream_t st) {
+    k_pass2b<<<b.n_win, 256, 0, st>>>(b);
+    return 1;
+}
+int launch_features_c1(const BatchView& b, cudaStream_t st) {
+    k_ref_lmax<<<(b.n_tgt + 127) / 128, 128, 0, st>>>(b);
+    k_scan_u32<<<1, 1024, 0, st>>>(b.w_nsup, b.w_supbase, b.n_win, b.counters, CNT_NSUP, 0, -1);
+    return 2;
+}
+int launch_features_c2(const BatchView& b, cudaStream_t st) {
+    k_fwd_list<<<b.n_win, 256, 0, st>>>(b);
+    return 1;
+}
+int launch_consensus(const BatchView& b, cudaStream_t st) {
+    k_cons_count<<<b.n_win, 256, 0, st>>>(b);
+    k_scan_u32<<<1, 1024, 0, st>>>(b.w_outlen, b.w_outoff, b.n_win, b.counters, CNT_TOTAL_OUT, 0, -1);
+    k_cons_write<<<b.n_win, 256, 0, st>>>(b);
+    return 3;
+}
+
+}  // namespace hb

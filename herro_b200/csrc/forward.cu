@@ -1,0 +1,286 @@
+// forward.cu — the neural forward at the informative (supported) positions only.
+//
+// Contract being replaced: src/inference.rs:147-175 — bases i32 [B,L,31], quals f32 [B,L,31]
+// (u8 * fl(2/93) - fl(66/93+1), two fp32 ops, H11), lens, indices ->
+// info_logits [sum lens], bases_logits [sum lens, 5].  The reference's TorchScript graph
+// evaluates its stem over every row of the padded batch tensor and then gathers `indices`;
+// because everything after the stem is local to one position (read-axis attention,
+// per-token FFN, read-axis collapse, heads), only the rows within the stem's receptive field
+// of a supported row are ever consumed.  This file therefore gathers FIRST: one work item per
+// supported row, reading the 2*(K/2)+1 neighbouring rows of the [L',32] token/quality matrix
+// straight from HBM, with the reference's batch-padding rows (token 11, qual byte 126 up to
+// the Lmax of the reference batch, zero beyond; H10) reproduced arithmetically.
+//
+// This is the fp32 SIMT implementation (bit-for-bit order-insensitive to ~1e-6 vs torch fp32).
+#include "common.cuh"
+#include "forward.h"
+
+namespace hb {
+
+constexpr int TOK_PER_POS = 32;  // 31 reads + 1 zero pad token, so that 4 positions = 128 rows
+
+// ---- stem: Embedding(12,6) ++ qual -> Conv(7->C, k=(K,1)) + bias + ReLU, + read_pos ---------
+// grid = positions, block = C threads (one output channel each).
+__global__ void k_stem(BatchView b, FwdWeights wt, uint32_t n0, uint32_t npos, float* __restrict__ X) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int K = wt.stem_k, C = wt.C;
+    uint8_t* s_tok = smem_raw;                          // [K][32]; 0xff = contributes nothing
+    float* s_q = (float*)(smem_raw + ((K * 32 + 15) & ~15));  // [K][32]
+    const uint32_t n = blockIdx.x;
+    if (n >= npos) return;
+    const uint32_t w = b.fwd_win[n0 + n], r = b.fwd_row[n0 + n];
+    const uint32_t L = b.w_L[w], Lref = b.w_reflmax[w];
+    const uint64_t rowbase = b.w_rowbase[w];
+    const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
+    for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+        const int j = i >> 5, c = i & 31;
+        const int64_t row = (int64_t)r + j - K / 2;
+        uint8_t tok = 0xff;
+        float q = 0.f;
+        if (c < R_COLS && row >= 0 && row < (int64_t)Lref) {
+            uint8_t qb;
+            if (row < (int64_t)L) {
+                tok = b.mat_bases[(rowbase + row) * ROW_BYTES + c];
+                qb = b.mat_quals[(rowbase + row) * ROW_BYTES + c];
+            } else {  // batch padding row of the reference's collate (src/inference.rs:86-97)
+                tok = (uint8_t)TOK_PAD;
+                qb = QUAL_PAD;
+            }
+            q = __fsub_rn(__fmul_rn((float)qb, QS), QO);
+        }
+        s_tok[i] = tok;
+        s_q[i] = q;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    const float bias = wt.stem_b[c];
+    float* xo = X + (size_t)n * TOK_PER_POS * C;
+    for (int rd = 0; rd < R_COLS; rd++) {
+        float acc = bias;
+        for (int j = 0; j < K; j++) {
+            const uint8_t tok = s_tok[j * 32 + rd];
+            if (tok != 0xff) {
+                acc += wt.stem_tab[((size_t)j * 12 + tok) * C + c];
+                acc = fmaf(s_q[j * 32 + rd], wt.stem_wq[(size_t)j * C + c], acc);
+            }
+        }
+        xo[(size_t)rd * C + c] = fmaxf(acc, 0.f) + wt.read_pos[(size_t)rd * C + c];
+    }
+    xo[(size_t)31 * C + c] = 0.f;
+}
+
+// ---- LayerNorm over C (eps 1e-5), one warp per token row --------------------------------------
+__global__ void k_layernorm(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ g,
+                            const float* __restrict__ be, uint32_t rows, int C) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = X + (size_t)row * C;
+    float s = 0.f;
+    for (int i = lane; i < C; i += 32) s += x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(HB_FULL, s, o);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int i = lane; i < C; i += 32) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HB_FULL, v, o);
+    const float rstd = rsqrtf(v / (float)C + 1e-5f);
+    float* y = Y + (size_t)row * C;
+    for (int i = lane; i < C; i += 32) y[i] = (x[i] - mean) * rstd * g[i] + be[i];
+}
+
+// ---- fp32 GEMM  Cout[M,N] = act(A[M,K] * Wt[N,K]^T + bias) (+ Res) -----------------------------
+// 128x64 tile, BK 16, 256 threads, 8x4 micro-tile.  M is padded by the caller to a multiple of 128
+// (buffers are allocated padded), N % 64 == 0, K % 16 == 0.
+template <int ACT, int RES>
+__global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Wt,
+                                              const float* __restrict__ bias, float* Cout, int ldc,
+                                              const float* Res, int K) {
+    __shared__ __align__(16) float As[16][128 + 4];
+    __shared__ __align__(16) float Ws[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    // load mapping: A tile 128 rows x 16 k = 512 float4: thread -> (row = tid/4 + 64*h, k4 = tid%4)
+    const int ar = tid >> 2, ak = (tid & 3) * 4;
+    const int wr = tid >> 2, wk = (tid & 3) * 4;  // W tile 64 rows x 16 k = 256 float4
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float4 v = *(const float4*)(A + (size_t)(m0 + ar + 64 * h) * lda + k0 + ak);
+            As[ak + 0][ar + 64 * h] = v.x; As[ak + 1][ar + 64 * h] = v.y;
+            As[ak + 2][ar + 64 * h] = v.z; As[ak + 3][ar + 64 * h] = v.w;
+        }
+        {
+            const float4 v = *(const float4*)(Wt + (size_t)(n0 + wr) * K + k0 + wk);
+            Ws[wk + 0][wr] = v.x; Ws[wk + 1][wr] = v.y; Ws[wk + 2][wr] = v.z; Ws[wk + 3][wr] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[8], wv[4];
+            const float4 a0 = *(const float4*)&As[kk][ty * 8], a1 = *(const float4*)&As[kk][ty * 8 + 4];
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            const float4 w0 = *(const float4*)&Ws[kk][tx * 4];
+            wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const float4 bv = *(const float4*)(bias + n0 + tx * 4);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const size_t o = (size_t)(m0 + ty * 8 + i) * ldc + n0 + tx * 4;
+        float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        if (ACT) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (RES) { const float4 r = *(const float4*)(Res + o); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        *(float4*)(Cout + o) = v;
+    }
+}
+
+// ---- read-axis multi-head attention: S = 31 tokens per position ----------------------------
+// one warp per (position, head); lane = query token; online softmax, all in registers.
+template <int DH>
+__global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, float* __restrict__ O, uint32_t npos,
+                                                   int C, int H) {
+    __shared__ float sK[4][32][DH + 1], sV[4][32][DH + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t item = blockIdx.x * 4 + warp;
+    if (item >= npos * (uint32_t)H) return;
+    const uint32_t n = item / H, h = item % H;
+    const float* base = QKV + (size_t)n * TOK_PER_POS * 3 * C;
+    // stage K and V of this head: 32 tokens x DH
+    for (int i = lane; i < 32 * DH; i += 32) {
+        const int t = i / DH, d = i % DH;
+        sK[warp][t][d] = base[(size_t)t * 3 * C + C + h * DH + d];
+        sV[warp][t][d] = base[(size_t)t * 3 * C + 2 * C + h * DH + d];
+    }
+    float q[DH], o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; d++) { q[d] = base[(size_t)lane * 3 * C + h * DH + d]; o[d] = 0.f; }
+    __syncwarp();
+    const float scale = rsqrtf((float)DH);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < R_COLS; j++) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d++) s = fmaf(q[d], sK[warp][j][d], s);
+        s *= scale;
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn), p = expf(s - mn);
+        l = l * corr + p;
+#pragma unroll
+        for (int d = 0; d < DH; d++) o[d] = fmaf(p, sV[warp][j][d], o[d] * corr);
+        m = mn;
+    }
+    const float inv = 1.f / l;
+    float* out = O + ((size_t)n * TOK_PER_POS + lane) * C + h * DH;
+    if (lane < R_COLS) {
+#pragma unroll
+        for (int d = 0; d < DH; d++) out[d] = o[d] * inv;
+    } else {
+#pragma unroll
+        for (int d = 0; d < DH; d++) out[d] = 0.f;
+    }
+}
+
+// ---- heads: base logits (5) + info logit (1), argmax (last maximal index wins, NaN greatest:
+//      Rust max_by_key over OrderedFloat, src/consensus.rs:136-141) written into row_emit. -----
+__device__ __forceinline__ bool of_less(float a, float b) {
+    if (isnan(a)) return false;
+    if (isnan(b)) return true;
+    return a < b;
+}
+__global__ void k_heads(BatchView b, FwdWeights wt, uint32_t n0, uint32_t npos, const float* __restrict__ Z,
+                        float* __restrict__ logits, float* __restrict__ info) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= npos) return;
+    const int D = wt.D;
+    const float* z = Z + (size_t)n * D;
+    float acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < D; i += 32) {
+        const float zv = z[i];
+#pragma unroll
+        for (int k = 0; k < 5; k++) acc[k] = fmaf(zv, wt.wb[(size_t)k * D + i], acc[k]);
+        acc[5] = fmaf(zv, wt.wi[i], acc[5]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(HB_FULL, acc[k], o);
+    if (lane == 0) {
+        float lg[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) { lg[k] = acc[k] + wt.bb[k]; logits[(size_t)(n0 + n) * 5 + k] = lg[k]; }
+        info[n0 + n] = acc[5] + wt.bi[0];
+        int am = 0;
+#pragma unroll
+        for (int k = 1; k < 5; k++) if (!of_less(lg[k], lg[am])) am = k;
+        const uint32_t w = b.fwd_win[n0 + n], r = b.fwd_row[n0 + n];
+        if (b.w_nsel[w] >= 2) b.row_emit[b.w_rowbase[w] + r] = (uint8_t)(am | 0x80);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos) {
+    const size_t np = (size_t)(chunk_pos + 127) / 128 * 128;  // positions padded to a GEMM tile
+    const size_t T = np * TOK_PER_POS;
+    return T * (size_t)(wt.C /*X*/ + wt.C /*H*/ + 3 * wt.C /*QKV*/ + wt.F /*F1*/) + np * wt.D /*Z*/;
+}
+
+template <int ACT, int RES>
+static void gemm(const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc, const float* Res,
+                 size_t M, int N, int K, cudaStream_t st) {
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)(N / 64));
+    k_gemm<ACT, RES><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+}
+
+// Runs positions [n0, n0+npos) of the work list.  Returns the number of kernel launches.
+int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, float* ws,
+                         float* logits, float* info, cudaStream_t st) {
+    const int C = wt.C, F = wt.F, D = wt.D, H = wt.H;
+    const size_t np_pad = (size_t)(npos + 127) / 128 * 128;
+    const size_t T = np_pad * TOK_PER_POS;
+    float* X = ws;
+    float* Hn = X + T * C;
+    float* QKV = Hn + T * C;
+    float* F1 = QKV + T * 3 * C;
+    float* Z = F1 + T * F;
+    int nl = 0;
+    // tokens of the pad positions of the last tile must be finite
+    if (T > (size_t)npos * TOK_PER_POS)
+        cudaMemsetAsync(X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
+    const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
+    k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, X); nl++;
+    const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
+    for (int l = 0; l < wt.layers; l++) {
+        const FwdLayer& ly = wt.layer[l];
+        k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); nl++;
+        gemm<0, 0>(Hn, C, ly.wqkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st); nl++;
+        const unsigned ab = (unsigned)(((size_t)npos * H + 3) / 4);
+        if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);
+        else k_attention<32><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);  // head_dim validated at load: 16 or 32
+        nl++;
+        gemm<0, 1>(Hn, C, ly.wo, ly.bo, X, C, X, T, C, C, st); nl++;
+        k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); nl++;
+        gemm<1, 0>(Hn, C, ly.w1, ly.b1, F1, F, nullptr, T, F, C, st); nl++;
+        gemm<0, 1>(F1, F, ly.w2, ly.b2, X, C, X, T, C, F, st); nl++;
+    }
+    k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); nl++;
+    // read-axis collapse: row n = the 31*C contiguous floats of position n (token 31 excluded)
+    gemm<1, 0>(Hn, TOK_PER_POS * C, wt.wc, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st); nl++;
+    k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, Z, logits, info); nl++;
+    return nl;
+}
+
+}  // namespace hb

@@ -1,0 +1,156 @@
+/* herro_b200.h — C ABI of the B200-native HERRO hot path (features -> inference -> consensus).
+ *
+ * The reference (lbcb-sci/herro @ 9cd0296) has no FFI layer: the three stages are Rust
+ * worker threads joined by crossbeam channels.  This header is what a `mod ffi` in the Rust
+ * host binds so that `herro inference` keeps its CLI, FASTQ loading, `--read-alns` batches,
+ * windowing and FASTA writer (src/main.rs, src/lib.rs, src/haec_io.rs, src/overlaps.rs,
+ * src/windowing.rs) and replaces
+ *
+ *   features::extract_features      src/features.rs:326-583   (called at src/lib.rs:176-183)
+ *   inference::inference_worker     src/inference.rs:177-212  (spawned at src/lib.rs:189-196)
+ *   consensus::consensus_worker     src/consensus.rs:229-263  (spawned at src/lib.rs:198-199)
+ *
+ * with calls into this library (INTEGRATION.md shows the Rust side).  Plain pointers and
+ * sizes only; no torch types; never unwinds or aborts (the reference is `panic = "abort"`,
+ * Cargo.toml:14-16): every entry point returns HB_OK or a negative hb_status, and
+ * hb_last_error() gives the message.
+ *
+ * Threading: hb_submit_* may be called concurrently from the host's feature threads
+ * (`-t`, src/lib.rs:159-187); hb_poll_corrected / hb_release_result from one thread per
+ * context (the former consensus thread feeding correction_writer, src/lib.rs:267-291).
+ * One context per GPU (`-d`), like the reference's per-device worker group.
+ */
+#ifndef HERRO_B200_H
+#define HERRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+typedef enum hb_status {
+    HB_OK = 0,
+    HB_ERR_ARG = -1,      /* bad argument / NULL pointer / out-of-range id                      */
+    HB_ERR_CUDA = -2,     /* CUDA runtime failure (no device, OOM, launch error)                */
+    HB_ERR_MODEL = -3,    /* weights file missing / malformed / unsupported dimensions          */
+    HB_ERR_INPUT = -4,    /* input on which the reference itself would panic (bad CIGAR, ...)   */
+    HB_ERR_CAPACITY = -5, /* an internal capacity was exceeded and could not be grown           */
+    HB_ERR_STATE = -6     /* call sequence error (e.g. submit before hb_upload_reads)           */
+} hb_status;
+
+/* Overlap + CIGAR of one alignment — `struct Overlap` / `struct Alignment`
+ * (src/overlaps.rs:44-55,91-95).  strand: 0 = '+', 1 = '-'.  cigar: ASCII `[0-9]+[MID]`
+ * exactly as parsed from the PAF `cg:Z:` field (src/overlaps.rs:172); caller-owned, copied
+ * before the call returns. */
+typedef struct hb_overlap {
+    uint32_t qid, qlen, qstart, qend;
+    uint32_t strand;
+    uint32_t tid, tlen, tstart, tend;
+    const uint8_t* cigar;
+    uint32_t cigar_len;
+} hb_overlap;
+
+/* One OverlapWindow (src/windowing.rs:6-16) plus the window it was pushed to
+ * (`windows[i].push(...)`, src/windowing.rs:161,233,262).  cigar_*_idx are BYTE offsets into
+ * the overlap's CIGAR, cigar_*_offset are base counts from the start of that op
+ * (SURVEY.md App. G). */
+typedef struct hb_overlap_window {
+    uint32_t overlap_idx; /* index into the `ovl` array of the same hb_submit_target call */
+    uint32_t window_idx;  /* 0 .. n_windows-1                                             */
+    uint32_t tstart, qstart, qend;
+    uint32_t cigar_start_idx, cigar_start_offset, cigar_end_idx, cigar_end_offset;
+} hb_overlap_window;
+
+typedef struct hb_options {
+    uint32_t struct_size;    /* = sizeof(hb_options)                                                     */
+    uint32_t window_size;    /* `-w` (src/main.rs:69-74), default 4096                                    */
+    uint32_t batch_size;     /* `-b` (src/main.rs:98-102): the reference groups consecutive windows of a  */
+                             /* read in chunks of b and pads each chunk to its longest window             */
+                             /* (src/features.rs:884-893, src/inference.rs:73-97); that padding is part   */
+                             /* of the model input, so it is reproduced per window       */
+    uint32_t launch_targets; /* target reads per device launch (cross-read batching); 0 = default         */
+    uint32_t flags;          /* HB_FLAG_*                                                                */
+} hb_options;
+
+#define HB_FLAG_KEEP_DEBUG 1u /* keep per-window intermediates of the last launch for hb_debug_*        */
+
+typedef struct hb_ctx hb_ctx; /* one per GPU: streams, weights, read-store replica, staging buffers */
+
+/* Create a context on `cuda_device` and load the forward weights (HB200W1 blob, see
+ * herro_b200/weights.py; replaces tch::CModule::load_on_device, src/inference.rs:185). */
+int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_options* opt);
+void hb_destroy(hb_ctx* ctx);
+
+/* Replicate the read store on the GPU.  Layout is HAECRecord verbatim (src/haec_io.rs:19-24,
+ * 77-81): seq_words[i] = 2-bit little-endian packing, 32 bases per u64, A0 C1 G2 T3
+ * (src/haec_io.rs:121-136); seq_len[i] bases; qual[i] = raw Phred+33 bytes (seq_len[i] of them).
+ * Read ids are positions in this array (`rid`), as in the reference (src/overlaps.rs:332-336). */
+int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_words, const uint32_t* seq_len,
+                    const uint8_t* const* qual);
+
+/* Submit one target read: the replacement of extract_features(rid, reads, overlaps, ...)
+ * (src/features.rs:326-333) for a host that still runs windowing::extract_windows itself.
+ * n_windows = ceil(len/W) (src/features.rs:338).  `ow` lists the OverlapWindows in the order
+ * extract_windows pushed them (alignment order), each tagged with its window.  Every
+ * overlap must have tid == rid (src/overlaps.rs:189-192).  Results become available through
+ * hb_poll_corrected after enough targets were submitted or after hb_flush. */
+int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
+                     const hb_overlap_window* ow, uint32_t n_ow);
+
+/* Same, but the library also performs windowing::extract_windows (src/windowing.rs:44-273)
+ * on the raw alignments — for hosts that hand over `(tid, Vec<Alignment>)` straight from
+ * alignment_reader (src/overlaps.rs:371-373). */
+int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl);
+
+/* Host-only utility (no context, no GPU): windowing::extract_windows (src/windowing.rs:44-273) of
+ * one alignment whose target has n_windows windows.  Writes up to `cap` records, returns the
+ * number produced in *n_out; HB_ERR_INPUT if the reference would panic on the alignment. */
+int hb_extract_windows(const hb_overlap* ovl, uint32_t overlap_idx, uint32_t window_size, uint32_t n_windows,
+                       hb_overlap_window* out, uint32_t cap, uint32_t* n_out);
+
+/* Launch whatever is pending and wait until every submitted target has a result queued. */
+int hb_flush(hb_ctx* ctx);
+
+/* Pop one finished target: the `(rid, Vec<Vec<u8>>)` of src/consensus.rs:253-257.
+ * Returns 1 and fills the outputs if a result was popped, 0 if none is queued, <0 on error.
+ * `*seqs` = the segments back to back (ASCII ACGT), `*seg_len[k]` their lengths; n_segs == 0
+ * means consensus() returned None or produced nothing — the read is omitted from the FASTA
+ * (src/consensus.rs:95-98, src/lib.rs:282-288).  Buffers stay valid until
+ * hb_release_result(ctx, *seqs). */
+int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg_len, uint32_t* n_segs);
+void hb_release_result(hb_ctx* ctx, uint8_t* seqs);
+
+const char* hb_last_error(hb_ctx* ctx); /* ctx may be NULL: error of a failed hb_create */
+
+/* ---- counters (the reference only has progress bars, src/pbars.rs) -------------------- */
+typedef struct hb_stats {
+    uint64_t targets, windows, overlap_windows, rows, supported, corrected_bases;
+    uint64_t h2d_bytes, d2h_bytes, kernel_launches, device_launches /* batches */;
+    double ms_features, ms_forward, ms_consensus; /* CUDA-event time, summed over launches */
+    double ms_pileup_kernel;                      /* the pileup-build kernel alone (roofline) */
+    uint64_t pileup_algo_bytes;                   /* algorithmic bytes it moved */
+} hb_stats;
+int hb_get_stats(hb_ctx* ctx, hb_stats* out);
+int hb_reset_stats(hb_ctx* ctx);
+
+/* ---- parity taps (need HB_FLAG_KEEP_DEBUG; valid for targets of the most recent launch) -- */
+/* shape4 = L' (rows), n_alns, n_supported, has_logits */
+int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* shape4);
+/* bases/quals: [L',31] u8 (tokens of BASES_MAP src/inference.rs:23-31 / raw quals), i.e. the
+ * arguments of FeaturesOutput::update after prepare_examples; supported: [n,2] u32 (pos, ins);
+ * sup_rows: [n] u32; info_logits [n], bases_logits [n,5] f32.  Any pointer may be NULL. */
+int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases, uint8_t* quals,
+                         uint32_t* supported, uint32_t* sup_rows, float* info_logits, float* bases_logits);
+
+/* ---- device-resident replay, used by bench.py for the HBM-resident `value` -------------- */
+/* Re-run all device stages of the most recent launch from its inputs already in HBM
+ * (no host<->device copies), `iters` times; returns the CUDA-event milliseconds in *ms. */
+int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERRO_B200_H */

@@ -1,0 +1,47 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact pileup matrices,
+supported positions and corrected segments; logits within 1e-3 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+LOGITS_TOL = 1e-3  # absolute, fp32 (BASELINE.json: "per-base logits match within 1e-3 fp32")
+
+
+@pytest.mark.parametrize("profile,seed", [("r10", 1), ("r9", 2)])
+def test_end_to_end_parity_w4096(profile, seed):
+    rs = helpers.small_readset(n_reads=40, mean_len=9000, seed=seed, profile=profile)
+    model = helpers.model_path(seed=3)
+    ora = helpers.run_oracle(rs, model, 4096, 64)
+    got = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    helpers.compare(ora, got, LOGITS_TOL)
+    assert got["stats"]["supported"] == sum(len(w.supported) for w in ora["windows"].values())
+
+
+def test_small_window_many_windows():
+    # -w is a runtime parameter (src/main.rs:69-74): W=512 gives ~20 windows per read, short last
+    # windows, reads split by uncovered windows, and batch groups (-b 4) smaller than a read.
+    rs = helpers.small_readset(n_reads=60, mean_len=6000, seed=5, coverage=12.0, min_ovl=600)
+    model = helpers.model_path(seed=4)
+    ora = helpers.run_oracle(rs, model, 512, 4)
+    got = helpers.run_product(rs, model, 512, 4, keep_debug=True)
+    helpers.compare(ora, got, LOGITS_TOL)
+
+
+def test_submit_target_equals_submit_alignments():
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=7)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64)
+    b = helpers.run_product(rs, model, 4096, 64, use_submit_target=True)
+    assert a["segments"] == b["segments"]
+
+
+def test_launch_batching_invariance():
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=8)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64, launch_targets=1 << 20)
+    b = helpers.run_product(rs, model, 4096, 64, launch_targets=3)
+    assert a["segments"] == b["segments"]
+    assert a["stats"]["device_launches"] == 1 and b["stats"]["device_launches"] > 1
