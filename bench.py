@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — corrected bases/s of the features -> inference -> consensus hot path.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference algorithm on the host cores)
+
+Workload (BASELINE.json configs[1], "cfg2"): synthetic 10k reads x 15 kb, R10 error profile,
+~40x coverage, `-b 64`, W = 4096.  One *step* = one device launch over `--launch-targets`
+consecutive target reads of that set (cross-read batching).  With N GPUs every rank owns one
+read cluster of the same size (the reference's `-c cluster` sharding): no
+collective on the data path, `scaling: weak`.
+
+Reported on ONE JSON line:
+  value      corrected bases/s, whole job, device stages only, inputs already resident in HBM
+             (hb_replay_last_launch; CUDA events on the launch stream)
+  e2e        the same metric through the public C ABI with host buffers: hb_submit_target x T ->
+             hb_flush -> hb_poll_corrected, H2D/D2H inside the timed region (host windowing and the
+             one-off read-store upload are the Rust host's job and are reported separately)
+  roofline   the dominant kernel class, timed live with CUDA events inside the library
+  cpu_baseline  the CPU oracle (a port: the reference is Rust and cannot be built here) + torch
+             fp32 forward on a bounded sample of the same targets
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corrected_bases_per_sec"
+UNIT = "bases/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10000)
+    ap.add_argument("--read-len", type=int, default=15000)
+    ap.add_argument("--profile", default="r10")
+    ap.add_argument("--window", type=int, default=4096)
+    ap.add_argument("--batch-size", type=int, default=64, help="reference -b")
+    ap.add_argument("--launch-targets", type=int, default=500)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_readset(args, rank):
+    from tools import synth
+    t0 = time.time()
+    rs = synth.generate(args.reads, args.read_len, profile=args.profile, seed=args.seed + 1000 * rank, coverage=40.0,
+                        min_ovl=2048)
+    return rs, time.time() - t0
+
+
+def cpu_reference_run(rs, model, targets, window, batch_size, threads):
+    """The reference algorithm on the host: C++ oracle (features, collate, consensus) on `threads`
+    workers + torch fp32 forward exactly as src/inference.rs:147-175 would call the model on CPU."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po, forward_ref
+    from herro_b200 import weights as hbw
+    torch.set_num_threads(threads)
+    reads = po.Reads(rs.ids, [rs.seq(i) for i in range(rs.n)], [rs.qual(i) for i in range(rs.n)])
+    cfg, tensors = hbw.load_blob(model)
+    net = forward_ref.from_weights(cfg, tensors)
+    t0 = time.time()
+
+    def feat(t):
+        ovl, cigs = rs.target_alns(t)
+        return t, (po.Target(reads, t, ovl, cigs, window, batch_size) if len(ovl) else None)
+
+    with ThreadPoolExecutor(threads) as ex:
+        T = list(ex.map(feat, targets))
+    t_feat = time.time() - t0
+    t1 = time.time()
+    for _, tg in T:
+        if tg is None:
+            continue
+        for b in range(tg.n_batches):
+            B = tg.batch(b)
+            info, bl = forward_ref.run_batch(net, B.bases, B.quals, B.lens, B.indices)
+            for k, wi in enumerate(B.win_index):
+                tg.set_logits(int(wi), info[k], bl[k])
+    t_fwd = time.time() - t1
+    t2 = time.time()
+    bases = 0
+    segs = {}
+    for t, tg in T:
+        if tg is None:
+            continue
+        s = tg.consensus()
+        segs[t] = s
+        bases += sum(len(x) for x in (s or []))
+    t_cons = time.time() - t2
+    return dict(bases=bases, seconds=time.time() - t0, t_features=t_feat, t_forward=t_fwd, t_consensus=t_cons, segments=segs)
+
+
+def ensure_model():
+    from herro_b200 import weights as hbw
+    d = os.path.join(ROOT, "tests", "_tmp")
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, f"bench_model_{os.getpid()}.hbw")
+    cfg = hbw.NetConfig()
+    hbw.save_blob(p, cfg, hbw.random_weights(cfg, seed=7))
+    return p, cfg
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    threads = os.cpu_count() or 1
+    workload = f"cfg2: synthetic {args.reads} reads x {args.read_len} bp, {args.profile} profile, 40x, W={args.window}, -b {args.batch_size}"
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        model, cfg = ensure_model()
+        rs, _ = make_readset(args, 0)
+        per = max(2, args.cpu_sample // 2)
+        need = (args.steps + args.warmup) * per
+        tg = [t for t in range(rs.n)][:need]
+        times, bases = [], 0
+        for s in range(args.warmup + args.steps):
+            r = cpu_reference_run(rs, model, tg[s * per:(s + 1) * per], args.window, args.batch_size, threads)
+            if s >= args.warmup:
+                times.append(r["seconds"])
+                bases += r["bases"]
+        tot = sum(times)
+        v = bases / tot
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": f"{per} target reads per step"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps x {per} target reads of the workload (CPU oracle + torch fp32 forward)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        os.remove(model)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (herro_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from herro_b200 import Context
+    from herro_b200 import api
+    model, cfg = ensure_model()
+    rs, t_gen = make_readset(args, rank)
+    n_steps = args.warmup + args.steps
+    lt = min(args.launch_targets, max(1, rs.n // n_steps))
+    # ---- host side that stays in the Rust binary: windowing (timed, outside the measured region)
+    t0 = time.time()
+    ovls, wins, nwin = {}, {}, {}
+    for t in range(n_steps * lt):
+        a0, a1 = int(rs.aln_off[t]), int(rs.aln_off[t + 1])
+        ovls[t] = Context.make_overlaps(rs.ovl9[a0:a1], rs.cigars, rs.cig_off[a0:a1 + 1])
+        nwin[t] = (int(rs.off[t + 1] - rs.off[t]) + args.window - 1) // args.window
+        wins[t] = api.extract_windows(ovls[t], args.window, nwin[t])
+    t_windowing = time.time() - t0
+
+    ctx = Context(model, local_rank, args.window, args.batch_size, launch_targets=1 << 30)
+    t0 = time.time()
+    ctx.upload_reads(rs.seqs, rs.quals, rs.off)
+    torch.cuda.synchronize()
+    t_upload = time.time() - t0
+
+    def e2e_step(s):
+        n = 0
+        for t in range(s * lt, (s + 1) * lt):
+            ctx.submit_target(t, nwin[t], ovls[t], wins[t])
+        ctx.flush()
+        for r in ctx.drain():
+            n += sum(len(x) for x in r.segments)
+        return n
+
+    for s in range(args.warmup):
+        e2e_step(s)
+    ctx.replay_last_launch(1)
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- region 1: end to end through the C ABI, host buffers, copies inside
+    barrier()
+    t0 = time.perf_counter()
+    bases_e2e, step_bases = 0, []
+    for s in range(args.warmup, n_steps):
+        step_bases.append(e2e_step(s))
+        bases_e2e += step_bases[-1]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    st = ctx.stats()
+    # ---- region 2: device stages only, inputs resident in HBM (one launch's working set is several
+    #      hundred MB of matrices + activations, larger than the 126 MB L2, so no L2 flush is needed)
+    barrier()
+    ms_dev = ctx.replay_last_launch(args.steps)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    st2 = ctx.stats()
+    # the replay re-runs the LAST timed launch `steps` times; its output size is known from region 1
+    per_step_bases = step_bases[-1]
+    t_dev = ms_dev / 1e3
+    vals = torch.tensor([t_dev, t_e2e, float(per_step_bases * args.steps), float(bases_e2e)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = vals.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = vals.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = float(tmax[0]), float(tmax[1])
+        bases_dev, bases_e2e_all = float(tsum[2]), float(tsum[3])
+    else:
+        bases_dev, bases_e2e_all = float(vals[2]), float(vals[3])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        mk, nk = st["ms_kernel"], st["n_kernel"]
+        top = max(mk, key=lambda k: mk[k])
+        gemm_tf = st["gemm_flops"] / (mk["gemm"] * 1e-3) / 1e12 if mk["gemm"] > 0 else 0.0
+        pile_gbs = st["pileup_algo_bytes"] / (mk["pileup"] * 1e-3) / 1e9 if mk["pileup"] > 0 else 0.0
+        if top == "gemm":
+            roof = {"kernel": "k_gemm (all dense contractions of the forward)", "bound": "tensor", "achieved": gemm_tf,
+                    "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak, "traffic": None, "peak_source": peak_src}
+        else:
+            roof = {"kernel": "k_pass2b (pileup build)", "bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": pile_gbs / hbm_peak, "traffic": None, "peak_source": peak_src}
+        out = {
+            "metric": METRIC, "value": bases_dev / t_dev, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 pileup/consensus + f32 forward", "data": "synthetic",
+            "config": {"workload": workload, "targets_per_step": lt, "windows_per_step": st["windows"] / max(st["device_launches"], 1),
+                       "supported_positions_per_step": st["supported"] / max(st["device_launches"], 1),
+                       "sharding": "one read cluster per GPU (read-id shard), no collective" if args.gpus > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (per-launch working set >> 126 MB)",
+                       "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
+                       "model": {"channels": cfg.channels, "heads": cfg.heads, "layers": cfg.layers, "ffn": cfg.ffn,
+                                 "stem_k": cfg.stem_k, "collapse": cfg.collapse, "weights": "random init (no checkpoint offline)"}},
+            "e2e": {"value": bases_e2e_all / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": st["h2d_bytes"] / max(st["device_launches"], 1),
+                    "d2h_bytes_per_step": st["d2h_bytes"] / max(st["device_launches"], 1)},
+            "gpu_launches": int(st2["kernel_launches"]),
+            "roofline": roof,
+            "kernels_ms_per_step": {k: mk[k] / max(st["device_launches"], 1) for k in mk if nk[k]},
+            "pileup_roofline": {"bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pile_gbs / hbm_peak},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and args.gpus == 1:
+            tg = list(range(args.warmup * lt, args.warmup * lt + args.cpu_sample))
+            r = cpu_reference_run(rs, model, tg, args.window, args.batch_size, threads)
+            out["cpu_baseline"] = {"value": r["bases"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{len(tg)} target reads of the workload; features {r['t_features']:.1f}s, "
+                                             f"forward {r['t_forward']:.1f}s, consensus {r['t_consensus']:.2f}s"}
+        print(json.dumps(out))
+    ctx.close()
+    try:
+        os.remove(model)
+    except OSError:
+        pass
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

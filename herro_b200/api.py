@@ -37,12 +37,16 @@ class HbOptions(C.Structure):
                 ("launch_targets", C.c_uint32), ("flags", C.c_uint32)]
 
 
+KERNEL_CLASSES = ["tokenize", "pass1", "scores", "pass2a", "scan", "pileup", "lists", "stem", "layernorm", "gemm",
+                  "attention", "heads", "consensus"]
+
+
 class HbStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("targets", "windows", "overlap_windows", "rows", "supported",
                                           "corrected_bases", "h2d_bytes", "d2h_bytes", "kernel_launches",
-                                          "device_launches")] + \
-               [(n, C.c_double) for n in ("ms_features", "ms_forward", "ms_consensus", "ms_pileup_kernel")] + \
-               [("pileup_algo_bytes", C.c_uint64)]
+                                          "device_launches", "pileup_algo_bytes", "gemm_flops", "forward_flops")] + \
+               [(n, C.c_double) for n in ("ms_features", "ms_forward", "ms_consensus")] + \
+               [("ms_kernel", C.c_double * 16), ("n_kernel", C.c_uint64 * 16)]
 
 
 class HerroError(RuntimeError):
@@ -114,14 +118,14 @@ def pack_2bit(seq: np.ndarray) -> np.ndarray:
     return np.bitwise_or.reduce(pad.reshape(nw, 32) << shifts, axis=1)
 
 
-def extract_windows(overlaps: np.ndarray, idx: int, window_size: int, n_windows: int) -> np.ndarray:
-    """Host-only windowing of overlaps[idx] (hb_extract_windows) -> OVERLAP_WINDOW_DTYPE array."""
+def extract_windows(overlaps: np.ndarray, window_size: int, n_windows: int) -> np.ndarray:
+    """Host-only windowing of all alignments of one target (hb_extract_windows) -> OVERLAP_WINDOW_DTYPE array."""
     L = load_library()
-    cap = n_windows + 2
+    cap = len(overlaps) * (n_windows + 1) + 1
     out = np.zeros(cap, dtype=OVERLAP_WINDOW_DTYPE)
     n = C.c_uint32()
-    rc = L.hb_extract_windows(overlaps.ctypes.data + idx * OVERLAP_DTYPE.itemsize, idx, window_size, n_windows,
-                              out.ctypes.data, cap, C.byref(n))
+    rc = L.hb_extract_windows(overlaps.ctypes.data, len(overlaps), window_size, n_windows, out.ctypes.data, cap,
+                              C.byref(n))
     if rc != 0:
         raise HerroError(rc, "alignment on which the reference would panic")
     return out[:n.value]
@@ -243,7 +247,10 @@ class Context:
     def stats(self) -> dict:
         s = HbStats()
         self._check(self._L.hb_get_stats(self._h, C.byref(s)))
-        return {n: getattr(s, n) for n, _ in HbStats._fields_}
+        d = {n: getattr(s, n) for n, _ in HbStats._fields_ if n not in ("ms_kernel", "n_kernel")}
+        d["ms_kernel"] = {k: s.ms_kernel[i] for i, k in enumerate(KERNEL_CLASSES)}
+        d["n_kernel"] = {k: int(s.n_kernel[i]) for i, k in enumerate(KERNEL_CLASSES)}
+        return d
 
     def reset_stats(self):
         self._check(self._L.hb_reset_stats(self._h))

@@ -127,6 +127,7 @@ struct hb_ctx {
     std::unordered_map<uint8_t*, void*> live;  // seqs pointer -> malloc block
     hb_stats stats{};
     LastLaunch last;
+    KTimer kt;
 };
 
 namespace {
@@ -360,14 +361,14 @@ int zero_scratch(hb_ctx* ctx, const BatchView& b) {
 
 // The forward + consensus part once the number of supported positions is known.
 int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launches) {
-    *launches += launch_features_c2(b, ctx->stream);
+    *launches += launch_features_c2(b, ctx->stream, ctx->kt);
     for (uint64_t n0 = 0; n0 < n_sup; n0 += ctx->chunk_pos) {
         const uint32_t np = (uint32_t)std::min<uint64_t>(ctx->chunk_pos, n_sup - n0);
         *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, ctx->d_ws.as<float>(), ctx->d_logits.as<float>(),
-                                          ctx->d_info.as<float>(), ctx->stream);
+                                          ctx->d_info.as<float>(), ctx->stream, ctx->kt);
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    *launches += launch_consensus(b, ctx->stream);
+    *launches += launch_consensus(b, ctx->stream, ctx->kt);
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     return HB_OK;
 }
@@ -401,16 +402,19 @@ int run_batch(hb_ctx* ctx) {
     uint64_t launches = 0;
     BatchView b;
     uint64_t total_rows = 0;
+    ctx->kt.on = true;
+    ctx->kt.st = ctx->stream;
     for (int attempt = 0;; attempt++) {
+        if (attempt) ctx->kt.discard();
         b = make_view(ctx, hbt);
         rc = zero_scratch(ctx, b);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        launches += launch_features_a(b, ctx->stream);
+        launches += launch_features_a(b, ctx->stream, ctx->kt);
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        launches += launch_pileup(b, ctx->stream);
+        launches += launch_pileup(b, ctx->stream, ctx->kt);
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-        launches += launch_features_c1(b, ctx->stream);  // ref_lmax + scan; the work list needs its buffers first
+        launches += launch_features_c1(b, ctx->stream, ctx->kt);  // ref_lmax + scan; the work list needs its buffers first
         CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         total_rows = (uint64_t)h_cnt[CNT_TOTAL_ROWS] | ((uint64_t)h_cnt[CNT_TOTAL_ROWS + 1] << 32);
@@ -454,9 +458,16 @@ int run_batch(hb_ctx* ctx) {
     // ---- timing
     float ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); ctx->stats.ms_features += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_pileup_kernel += ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_forward += ms;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->stats.ms_consensus += ms;
+    ctx->kt.collect(ctx->stats.ms_kernel, ctx->stats.n_kernel);
+    ctx->kt.on = false;
+    {
+        uint64_t gf = 0;
+        const uint64_t ff = forward_flops_per_pos(ctx->wt, &gf);
+        ctx->stats.forward_flops += ff * n_sup;
+        ctx->stats.gemm_flops += gf * n_sup;
+    }
 
     // ---- per-read reassembly (src/consensus.rs:90-111,222-226)
     const uint8_t* outb = ctx->pin_out.as<uint8_t>();
@@ -644,6 +655,7 @@ void hb_destroy(hb_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->pin_in.release(); ctx->pin_small.release(); ctx->pin_out.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    ctx->kt.destroy();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     for (auto& kv : ctx->live) free(kv.second);
     delete ctx;
@@ -741,11 +753,12 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
     return append_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
 }
 
-int hb_extract_windows(const hb_overlap* ovl, uint32_t overlap_idx, uint32_t window_size, uint32_t n_windows,
+int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
                        hb_overlap_window* out, uint32_t cap, uint32_t* n_out) {
-    if (!ovl || !n_out || window_size == 0) return HB_ERR_ARG;
+    if ((!ovl && n_ovl) || !n_out || window_size == 0) return HB_ERR_ARG;
     std::vector<hb_overlap_window> v;
-    if (host_extract_windows(*ovl, overlap_idx, window_size, n_windows, v) != 0) return HB_ERR_INPUT;
+    for (uint32_t i = 0; i < n_ovl; i++)
+        if (host_extract_windows(ovl[i], i, window_size, n_windows, v) != 0) return HB_ERR_INPUT;
     *n_out = (uint32_t)v.size();
     if (out) memcpy(out, v.data(), std::min<size_t>(v.size(), cap) * sizeof(hb_overlap_window));
     return HB_OK;
@@ -862,20 +875,23 @@ int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {
     if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch to replay");
     const BatchView b = ctx->last.view;
     uint64_t launches = 0;
+    ctx->kt.on = false;
+    ctx->kt.st = ctx->stream;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     for (uint32_t it = 0; it < iters; it++) {
         int rc = zero_scratch(ctx, b);
         if (rc) return rc;
-        launches += launch_features_a(b, ctx->stream);
-        launches += launch_pileup(b, ctx->stream);
-        launches += launch_features_c1(b, ctx->stream);
+        launches += launch_features_a(b, ctx->stream, ctx->kt);
+        launches += launch_pileup(b, ctx->stream, ctx->kt);
+        launches += launch_features_c1(b, ctx->stream, ctx->kt);
         rc = launch_tail(ctx, b, ctx->last.n_sup, &launches);
         if (rc) return rc;
     }
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
+    ctx->kt.discard();
     ctx->stats.kernel_launches += launches;
     return HB_OK;
 }

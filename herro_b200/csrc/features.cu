@@ -15,6 +15,7 @@
 //   consensus (src/consensus.rs:176-217, the majority vote) are evaluated on the tile while
 //   it is still in shared memory.
 #include "common.cuh"
+#include "forward.h"
 
 namespace hb {
 
@@ -701,32 +702,34 @@ cudaError_t features_configure(uint32_t W) {
     return cudaFuncSetAttribute(k_pass2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2a_smem(W));
 }
 
-int launch_features_a(const BatchView& b, cudaStream_t st) {
+int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
     int n = 0;
-    if (b.n_ow) { k_tokenize<<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); n++; }
-    k_pass1<<<b.n_win, 256, pass1_smem(b.W), st>>>(b); n++;
-    if (b.n_ovl) { k_scores<<<(b.n_ovl + 255) / 256, 256, 0, st>>>(b); n++; }
-    k_pass2a<<<b.n_win, 256, pass2a_smem(b.W), st>>>(b); n++;
-    k_scan_u32<<<1, 1024, 0, st>>>(b.w_L, b.w_rowbase, b.n_win, b.counters, CNT_TOTAL_ROWS, b.rows_cap, CNT_OVERFLOW); n++;
+    if (b.n_ow) { kt.begin(K_TOKENIZE); k_tokenize<<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); kt.end(); n++; }
+    kt.begin(K_PASS1); k_pass1<<<b.n_win, 256, pass1_smem(b.W), st>>>(b); kt.end(); n++;
+    if (b.n_ovl) { kt.begin(K_SCORES); k_scores<<<(b.n_ovl + 255) / 256, 256, 0, st>>>(b); kt.end(); n++; }
+    kt.begin(K_PASS2A); k_pass2a<<<b.n_win, 256, pass2a_smem(b.W), st>>>(b); kt.end(); n++;
+    kt.begin(K_SCAN);
+    k_scan_u32<<<1, 1024, 0, st>>>(b.w_L, b.w_rowbase, b.n_win, b.counters, CNT_TOTAL_ROWS, b.rows_cap, CNT_OVERFLOW);
+    kt.end(); n++;
     return n;
 }
-int launch_pileup(const BatchView& b, cudaStream_t st) {
-    k_pass2b<<<b.n_win, 256, 0, st>>>(b);
+int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt) {
+    kt.begin(K_PILEUP); k_pass2b<<<b.n_win, 256, 0, st>>>(b); kt.end();
     return 1;
 }
-int launch_features_c1(const BatchView& b, cudaStream_t st) {
-    k_ref_lmax<<<(b.n_tgt + 127) / 128, 128, 0, st>>>(b);
-    k_scan_u32<<<1, 1024, 0, st>>>(b.w_nsup, b.w_supbase, b.n_win, b.counters, CNT_NSUP, 0, -1);
+int launch_features_c1(const BatchView& b, cudaStream_t st, KTimer& kt) {
+    kt.begin(K_LISTS); k_ref_lmax<<<(b.n_tgt + 127) / 128, 128, 0, st>>>(b); kt.end();
+    kt.begin(K_SCAN); k_scan_u32<<<1, 1024, 0, st>>>(b.w_nsup, b.w_supbase, b.n_win, b.counters, CNT_NSUP, 0, -1); kt.end();
     return 2;
 }
-int launch_features_c2(const BatchView& b, cudaStream_t st) {
-    k_fwd_list<<<b.n_win, 256, 0, st>>>(b);
+int launch_features_c2(const BatchView& b, cudaStream_t st, KTimer& kt) {
+    kt.begin(K_LISTS); k_fwd_list<<<b.n_win, 256, 0, st>>>(b); kt.end();
     return 1;
 }
-int launch_consensus(const BatchView& b, cudaStream_t st) {
-    k_cons_count<<<b.n_win, 256, 0, st>>>(b);
-    k_scan_u32<<<1, 1024, 0, st>>>(b.w_outlen, b.w_outoff, b.n_win, b.counters, CNT_TOTAL_OUT, 0, -1);
-    k_cons_write<<<b.n_win, 256, 0, st>>>(b);
+int launch_consensus(const BatchView& b, cudaStream_t st, KTimer& kt) {
+    kt.begin(K_CONSENSUS); k_cons_count<<<b.n_win, 256, 0, st>>>(b); kt.end();
+    kt.begin(K_SCAN); k_scan_u32<<<1, 1024, 0, st>>>(b.w_outlen, b.w_outoff, b.n_win, b.counters, CNT_TOTAL_OUT, 0, -1); kt.end();
+    kt.begin(K_CONSENSUS); k_cons_write<<<b.n_win, 256, 0, st>>>(b); kt.end();
     return 3;
 }
 

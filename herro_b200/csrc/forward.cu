@@ -240,14 +240,29 @@ size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos) {
 
 template <int ACT, int RES>
 static void gemm(const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc, const float* Res,
-                 size_t M, int N, int K, cudaStream_t st) {
+                 size_t M, int N, int K, cudaStream_t st, KTimer& kt) {
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)(N / 64));
+    kt.begin(K_GEMM);
     k_gemm<ACT, RES><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+    kt.end();
+}
+
+// algorithmic FLOPs per supported position (2 * MACs), and the part that is dense contractions
+uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops) {
+    const uint64_t C = wt.C, F = wt.F, D = wt.D, K = wt.stem_k, S = R_COLS, dh = wt.C / wt.H;
+    const uint64_t stem = S * K * 7 * C * 2;
+    const uint64_t per_layer_gemm = S * 2 * (C * 3 * C + C * C + 2 * C * F);
+    const uint64_t per_layer_attn = (uint64_t)wt.H * 2 * 2 * S * S * dh;
+    const uint64_t collapse = 2 * S * C * D;
+    const uint64_t heads = 2 * D * 6;
+    const uint64_t g = (uint64_t)wt.layers * per_layer_gemm + collapse;
+    if (gemm_flops) *gemm_flops = g;
+    return stem + g + (uint64_t)wt.layers * per_layer_attn + heads;
 }
 
 // Runs positions [n0, n0+npos) of the work list.  Returns the number of kernel launches.
 int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, float* ws,
-                         float* logits, float* info, cudaStream_t st) {
+                         float* logits, float* info, cudaStream_t st, KTimer& kt) {
     const int C = wt.C, F = wt.F, D = wt.D, H = wt.H;
     const size_t np_pad = (size_t)(npos + 127) / 128 * 128;
     const size_t T = np_pad * TOK_PER_POS;
@@ -261,25 +276,28 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     if (T > (size_t)npos * TOK_PER_POS)
         cudaMemsetAsync(X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
     const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
-    k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, X); nl++;
+    kt.begin(K_STEM); k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, X); kt.end(); nl++;
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
-        k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); nl++;
-        gemm<0, 0>(Hn, C, ly.wqkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st); nl++;
+        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); kt.end(); nl++;
+        gemm<0, 0>(Hn, C, ly.wqkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st, kt); nl++;
         const unsigned ab = (unsigned)(((size_t)npos * H + 3) / 4);
+        kt.begin(K_ATTENTION);
         if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);
         else k_attention<32><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);  // head_dim validated at load: 16 or 32
-        nl++;
-        gemm<0, 1>(Hn, C, ly.wo, ly.bo, X, C, X, T, C, C, st); nl++;
-        k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); nl++;
-        gemm<1, 0>(Hn, C, ly.w1, ly.b1, F1, F, nullptr, T, F, C, st); nl++;
-        gemm<0, 1>(F1, F, ly.w2, ly.b2, X, C, X, T, C, F, st); nl++;
+        kt.end(); nl++;
+        gemm<0, 1>(Hn, C, ly.wo, ly.bo, X, C, X, T, C, C, st, kt); nl++;
+        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
+        gemm<1, 0>(Hn, C, ly.w1, ly.b1, F1, F, nullptr, T, F, C, st, kt); nl++;
+        gemm<0, 1>(F1, F, ly.w2, ly.b2, X, C, X, T, C, F, st, kt); nl++;
     }
-    k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); nl++;
+    kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); kt.end(); nl++;
     // read-axis collapse: row n = the 31*C contiguous floats of position n (token 31 excluded)
-    gemm<1, 0>(Hn, TOK_PER_POS * C, wt.wc, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st); nl++;
-    k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, Z, logits, info); nl++;
+    gemm<1, 0>(Hn, TOK_PER_POS * C, wt.wc, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st, kt); nl++;
+    kt.begin(K_HEADS);
+    k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, Z, logits, info);
+    kt.end(); nl++;
     return nl;
 }
 

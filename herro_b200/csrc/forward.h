@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "common.cuh"
 
 namespace hb {
@@ -23,16 +24,54 @@ struct FwdWeights {
     const float *lnf_g, *lnf_b, *wc, *bc, *wb, *bb, *wi, *bi;
 };
 
+// Per-kernel-class CUDA-event timing on the launching stream (off during replays).
+struct KTimer {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int cls; size_t e0, e1; };
+    std::vector<Rec> recs;
+    uint64_t launches[16] = {0};
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void begin(int cls) {
+        launches[cls]++;
+        if (!on) return;
+        recs.push_back(Rec{cls, used, used + 1});
+        cudaEventRecord(get(), st);
+        get();
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(pool[recs.back().e1], st);
+    }
+    // after the stream is synchronised: add elapsed ms per class, reset
+    void collect(double* ms, uint64_t* n) {
+        for (auto& r : recs) { float t = 0; cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]); ms[r.cls] += t; }
+        for (int i = 0; i < 16; i++) { n[i] += launches[i]; launches[i] = 0; }
+        recs.clear();
+        used = 0;
+    }
+    void discard() { for (auto& l : launches) l = 0; recs.clear(); used = 0; }
+    void destroy() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+enum { K_TOKENIZE = 0, K_PASS1, K_SCORES, K_PASS2A, K_SCAN, K_PILEUP, K_LISTS, K_STEM, K_LAYERNORM, K_GEMM, K_ATTENTION,
+       K_HEADS, K_CONSENSUS };
+
 size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos);
 int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, float* ws,
-                         float* logits, float* info, cudaStream_t st);
+                         float* logits, float* info, cudaStream_t st, KTimer& kt);
+uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops);
 
 // features.cu
 cudaError_t features_configure(uint32_t W);
-int launch_features_a(const BatchView& b, cudaStream_t st);
-int launch_pileup(const BatchView& b, cudaStream_t st);
-int launch_features_c1(const BatchView& b, cudaStream_t st);
-int launch_features_c2(const BatchView& b, cudaStream_t st);
-int launch_consensus(const BatchView& b, cudaStream_t st);
+int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt);
+int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt);
+int launch_features_c1(const BatchView& b, cudaStream_t st, KTimer& kt);
+int launch_features_c2(const BatchView& b, cudaStream_t st, KTimer& kt);
+int launch_consensus(const BatchView& b, cudaStream_t st, KTimer& kt);
 
 }  // namespace hb

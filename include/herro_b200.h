@@ -106,9 +106,10 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl);
 
 /* Host-only utility (no context, no GPU): windowing::extract_windows (src/windowing.rs:44-273) of
- * one alignment whose target has n_windows windows.  Writes up to `cap` records, returns the
- * number produced in *n_out; HB_ERR_INPUT if the reference would panic on the alignment. */
-int hb_extract_windows(const hb_overlap* ovl, uint32_t overlap_idx, uint32_t window_size, uint32_t n_windows,
+ * the n_ovl alignments of one target that has n_windows windows (overlap_idx = position in
+ * `ovl`).  Writes up to `cap` records in push order, returns the number produced in *n_out
+ * (may exceed cap: call again with a larger buffer); HB_ERR_INPUT if the reference would panic. */
+int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
                        hb_overlap_window* out, uint32_t cap, uint32_t* n_out);
 
 /* Launch whatever is pending and wait until every submitted target has a result queued. */
@@ -126,12 +127,19 @@ void hb_release_result(hb_ctx* ctx, uint8_t* seqs);
 const char* hb_last_error(hb_ctx* ctx); /* ctx may be NULL: error of a failed hb_create */
 
 /* ---- counters (the reference only has progress bars, src/pbars.rs) -------------------- */
+#define HB_NUM_KERNEL_CLASSES 16
+/* kernel classes of ms_kernel[] / n_kernel[] */
+enum { HB_K_TOKENIZE = 0, HB_K_PASS1, HB_K_SCORES, HB_K_PASS2A, HB_K_SCAN, HB_K_PILEUP, HB_K_LISTS, HB_K_STEM,
+       HB_K_LAYERNORM, HB_K_GEMM, HB_K_ATTENTION, HB_K_HEADS, HB_K_CONSENSUS };
 typedef struct hb_stats {
     uint64_t targets, windows, overlap_windows, rows, supported, corrected_bases;
     uint64_t h2d_bytes, d2h_bytes, kernel_launches, device_launches /* batches */;
-    double ms_features, ms_forward, ms_consensus; /* CUDA-event time, summed over launches */
-    double ms_pileup_kernel;                      /* the pileup-build kernel alone (roofline) */
-    uint64_t pileup_algo_bytes;                   /* algorithmic bytes it moved */
+    uint64_t pileup_algo_bytes; /* algorithmic bytes of the pileup-build kernel */
+    uint64_t gemm_flops;        /* algorithmic FLOPs of the dense contractions (QKV/out/FFN/collapse)     */
+    uint64_t forward_flops;     /* all forward FLOPs at the supported positions                            */
+    double ms_features, ms_forward, ms_consensus;  /* CUDA-event time per stage, summed over launches      */
+    double ms_kernel[HB_NUM_KERNEL_CLASSES];       /* CUDA-event time per kernel class (timed launches)    */
+    uint64_t n_kernel[HB_NUM_KERNEL_CLASSES];      /* launches per kernel class                            */
 } hb_stats;
 int hb_get_stats(hb_ctx* ctx, hb_stats* out);
 int hb_reset_stats(hb_ctx* ctx);
