@@ -86,13 +86,25 @@ def load_library():
     L.hb_debug_window_shape.argtypes = [vp, u32, u32, u32p]
     L.hb_debug_dump_window.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp]
     L.hb_replay_last_launch.argtypes = [vp, u32, C.POINTER(C.c_float)]
+    fp = C.POINTER(C.c_float)
+    L.hb_selftest_gemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, C.c_int, u32, fp, fp, fp, fp]
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = ["hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
-                    "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch"]
+                    "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
+
+
+def selftest_gemm(M, N, K, act=0, res=0, lda_extra=0, device=0):
+    """-> dict(max_abs_err, max_abs_ref, ms_tc, ms_simt): tcgen05 bf16x3 contraction vs fp32 SIMT."""
+    L = load_library()
+    v = [C.c_float() for _ in range(4)]
+    rc = L.hb_selftest_gemm(device, M, N, K, act, res, lda_extra, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise HerroError(rc, L.hb_last_error(None).decode())
+    return dict(max_abs_err=v[0].value, max_abs_ref=v[1].value, ms_tc=v[2].value, ms_simt=v[3].value)
 
 
 # ------------------------------------------------------------------------------------------

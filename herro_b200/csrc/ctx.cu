@@ -240,6 +240,24 @@ int load_weights(hb_ctx* ctx, const char* path) {
          get("bc", D, wt.bc) && get("wb", 5 * (size_t)D, wt.wb) && get("bb", 5, wt.bb) && get("wi", D, wt.wi) &&
          get("bi", 1, wt.bi);
     if (!ok) return ctx->err.rfind("cuda", 0) == 0 ? HB_ERR_CUDA : HB_ERR_MODEL;
+    // bf16 hi/lo split of the contraction weights for the tcgen05 path (gemm_tc.cu)
+    const char* mode = getenv("HERRO_B200_GEMM");
+    wt.use_tc = !(mode && std::string(mode) == "simt");
+    auto split = [&](const float* w, size_t n, SplitW& s) -> bool {
+        void *hi = nullptr, *lo = nullptr;
+        if (split_weights(w, n, &hi, &lo) != cudaSuccess) { ctx->err = "cuda: weight split failed"; return false; }
+        ctx->weight_allocs.push_back(hi);
+        ctx->weight_allocs.push_back(lo);
+        s.hi = hi; s.lo = lo;
+        return true;
+    };
+    for (int l = 0; l < wt.layers; l++) {
+        FwdLayer& ly = wt.layer[l];
+        if (!split(ly.wqkv, (size_t)3 * C * C, ly.s_qkv) || !split(ly.wo, (size_t)C * C, ly.s_o) ||
+            !split(ly.w1, (size_t)F * C, ly.s_1) || !split(ly.w2, (size_t)C * F, ly.s_2)) return HB_ERR_CUDA;
+    }
+    if (!split(wt.wc, (size_t)D * 31 * C, wt.s_c)) return HB_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "cuda: weight split kernel failed"; return HB_ERR_CUDA; }
     return HB_OK;
 }
 
@@ -866,6 +884,66 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
         if (bases_logits) CK(cudaMemcpy(bases_logits, ctx->d_logits.as<float>() + sb * 5, (size_t)ns * 20, cudaMemcpyDeviceToHost));
     }
     return HB_OK;
+}
+
+int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int act, int res, uint32_t lda_extra,
+                     float* max_abs_err, float* max_abs_ref, float* ms_tc, float* ms_simt) {
+    if (!max_abs_err || !max_abs_ref || M % 128 || N % 64 || K % 64) return HB_ERR_ARG;
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return HB_ERR_CUDA;
+    const size_t lda = (size_t)K + lda_extra;
+    std::vector<float> hA((size_t)M * lda), hW((size_t)N * K), hb(N), hR((size_t)M * N);
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((double)(s >> 11) / 9007199254740992.0 * 2.0 - 1.0); };
+    for (auto& v : hA) v = rnd();
+    for (auto& v : hW) v = rnd() * 0.1f;
+    for (auto& v : hb) v = rnd();
+    for (auto& v : hR) v = rnd();
+    float *dA, *dW, *db, *dR, *dC1, *dC2;
+    void *hi = nullptr, *lo = nullptr;
+    bool ok = cudaMalloc(&dA, hA.size() * 4) == cudaSuccess && cudaMalloc(&dW, hW.size() * 4) == cudaSuccess &&
+              cudaMalloc(&db, hb.size() * 4) == cudaSuccess && cudaMalloc(&dR, hR.size() * 4) == cudaSuccess &&
+              cudaMalloc(&dC1, hR.size() * 4) == cudaSuccess && cudaMalloc(&dC2, hR.size() * 4) == cudaSuccess;
+    if (!ok) return HB_ERR_CUDA;
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dR, hR.data(), hR.size() * 4, cudaMemcpyHostToDevice);
+    if (split_weights(dW, hW.size(), &hi, &lo) != cudaSuccess) return HB_ERR_CUDA;
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 2; rep++) {  // second repetition is the timed one
+        cudaEventRecord(e0);
+        gemm_simt(act, res, dA, (int)lda, dW, db, dC1, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
+        cudaEventRecord(e1);
+        e = gemm_tc(act, res, dA, (int)lda, hi, lo, db, dC2, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
+        cudaEventRecord(e2);
+        if (e != cudaSuccess) break;
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) break;
+    }
+    int rc = HB_OK;
+    if (e != cudaSuccess) {
+        g_create_err = std::string("selftest: ") + cudaGetErrorString(e);
+        rc = HB_ERR_CUDA;
+    } else {
+        std::vector<float> c1(hR.size()), c2(hR.size());
+        cudaMemcpy(c1.data(), dC1, c1.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(c2.data(), dC2, c2.size() * 4, cudaMemcpyDeviceToHost);
+        float me = 0, mr = 0;
+        for (size_t i = 0; i < c1.size(); i++) {
+            float d = fabsf(c1[i] - c2[i]);
+            if (!(d <= me)) me = d;  // NaN propagates
+            mr = std::max(mr, fabsf(c1[i]));
+        }
+        *max_abs_err = me;
+        *max_abs_ref = mr;
+        if (ms_simt) cudaEventElapsedTime(ms_simt, e0, e1);
+        if (ms_tc) cudaEventElapsedTime(ms_tc, e1, e2);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dR); cudaFree(dC1); cudaFree(dC2); cudaFree(hi); cudaFree(lo);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
 }
 
 int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {

@@ -238,12 +238,20 @@ size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos) {
     return T * (size_t)(wt.C /*X*/ + wt.C /*H*/ + 3 * wt.C /*QKV*/ + wt.F /*F1*/) + np * wt.D /*Z*/;
 }
 
-template <int ACT, int RES>
-static void gemm(const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc, const float* Res,
-                 size_t M, int N, int K, cudaStream_t st, KTimer& kt) {
+void gemm_simt(int act, int res, const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc,
+               const float* Res, size_t M, int N, int K, cudaStream_t st) {
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)(N / 64));
+    if (act == 0 && res == 0) k_gemm<0, 0><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+    else if (act == 1 && res == 0) k_gemm<1, 0><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+    else k_gemm<0, 1><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+}
+
+template <int ACT, int RES>
+static void gemm(const FwdWeights& wt, const float* A, int lda, const float* Wt, const SplitW& sw, const float* bias,
+                 float* Cout, int ldc, const float* Res, size_t M, int N, int K, cudaStream_t st, KTimer& kt) {
     kt.begin(K_GEMM);
-    k_gemm<ACT, RES><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
+    if (wt.use_tc && sw.hi) gemm_tc(ACT, RES, A, lda, sw.hi, sw.lo, bias, Cout, ldc, Res, M, N, K, st);
+    else gemm_simt(ACT, RES, A, lda, Wt, bias, Cout, ldc, Res, M, N, K, st);
     kt.end();
 }
 
@@ -281,20 +289,20 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
         kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); kt.end(); nl++;
-        gemm<0, 0>(Hn, C, ly.wqkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st, kt); nl++;
+        gemm<0, 0>(wt, Hn, C, ly.wqkv, ly.s_qkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st, kt); nl++;
         const unsigned ab = (unsigned)(((size_t)npos * H + 3) / 4);
         kt.begin(K_ATTENTION);
         if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);
         else k_attention<32><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);  // head_dim validated at load: 16 or 32
         kt.end(); nl++;
-        gemm<0, 1>(Hn, C, ly.wo, ly.bo, X, C, X, T, C, C, st, kt); nl++;
+        gemm<0, 1>(wt, Hn, C, ly.wo, ly.s_o, ly.bo, X, C, X, T, C, C, st, kt); nl++;
         kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
-        gemm<1, 0>(Hn, C, ly.w1, ly.b1, F1, F, nullptr, T, F, C, st, kt); nl++;
-        gemm<0, 1>(F1, F, ly.w2, ly.b2, X, C, X, T, C, F, st, kt); nl++;
+        gemm<1, 0>(wt, Hn, C, ly.w1, ly.s_1, ly.b1, F1, F, nullptr, T, F, C, st, kt); nl++;
+        gemm<0, 1>(wt, F1, F, ly.w2, ly.s_2, ly.b2, X, C, X, T, C, F, st, kt); nl++;
     }
     kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); kt.end(); nl++;
     // read-axis collapse: row n = the 31*C contiguous floats of position n (token 31 excluded)
-    gemm<1, 0>(Hn, TOK_PER_POS * C, wt.wc, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st, kt); nl++;
+    gemm<1, 0>(wt, Hn, TOK_PER_POS * C, wt.wc, wt.s_c, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st, kt); nl++;
     kt.begin(K_HEADS);
     k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, Z, logits, info);
     kt.end(); nl++;

@@ -10,8 +10,13 @@ namespace hb {
 
 constexpr int MAX_LAYERS = 8;
 
+struct SplitW {  // bf16 hi / lo split of an fp32 weight matrix [N,K] (gemm_tc.cu)
+    const void *hi = nullptr, *lo = nullptr;
+};
+
 struct FwdLayer {
     const float *ln1_g, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+    SplitW s_qkv, s_o, s_1, s_2;
 };
 
 struct FwdWeights {
@@ -22,7 +27,17 @@ struct FwdWeights {
     const float* read_pos;  // [31][C]
     FwdLayer layer[MAX_LAYERS];
     const float *lnf_g, *lnf_b, *wc, *bc, *wb, *bb, *wi, *bi;
+    SplitW s_c;
+    int use_tc;  // 1: tcgen05 bf16x3 contractions (default), 0: fp32 SIMT (HERRO_B200_GEMM=simt)
 };
+
+// gemm_tc.cu
+cudaError_t split_weights(const float* w, size_t n, void** hi, void** lo);
+cudaError_t gemm_tc(int act, int res, const float* A, int lda, const void* Whi, const void* Wlo, const float* bias, float* Cout,
+                    int ldc, const float* Res, size_t M, int N, int K, cudaStream_t st);
+// forward.cu (fp32 SIMT reference contraction, also used by the self test)
+void gemm_simt(int act, int res, const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc,
+               const float* Res, size_t M, int N, int K, cudaStream_t st);
 
 // Per-kernel-class CUDA-event timing on the launching stream (off during replays).
 struct KTimer {
