@@ -180,8 +180,8 @@ int load_weights(hb_ctx* ctx, const char* path) {
     wt.stem_k = (int)h.cfg[3]; wt.C = (int)h.cfg[4]; wt.H = (int)h.cfg[5]; wt.layers = (int)h.cfg[6];
     wt.F = (int)h.cfg[7]; wt.D = (int)h.cfg[8];
     if (wt.layers < 1 || wt.layers > MAX_LAYERS || wt.H < 1 || wt.C % wt.H || (wt.C / wt.H != 16 && wt.C / wt.H != 32) ||
-        wt.C % 64 || wt.F % 64 || wt.D % 64 || !(wt.stem_k & 1) || wt.stem_k > 129 || wt.C > 1024)
-        return fail(ctx, HB_ERR_MODEL, "unsupported model dimensions (need C,F,D % 64 == 0, head_dim 16 or 32, odd stem_k)");
+        wt.C % 128 || wt.F % 128 || wt.D % 128 || !(wt.stem_k & 1) || wt.stem_k > 129 || wt.C > 1024)
+        return fail(ctx, HB_ERR_MODEL, "unsupported model dimensions (need C,F,D % 128 == 0, head_dim 16 or 32, odd stem_k)");
     std::unordered_map<std::string, std::pair<const float*, size_t>> T;
     for (uint32_t i = 0; i < h.n_tensors; i++) {
         BlobEntry e;
@@ -241,8 +241,7 @@ int load_weights(hb_ctx* ctx, const char* path) {
          get("bi", 1, wt.bi);
     if (!ok) return ctx->err.rfind("cuda", 0) == 0 ? HB_ERR_CUDA : HB_ERR_MODEL;
     // bf16 hi/lo split of the contraction weights for the tcgen05 path (gemm_tc.cu)
-    const char* mode = getenv("HERRO_B200_GEMM");
-    wt.use_tc = !(mode && std::string(mode) == "simt");
+    if (cudaDeviceGetAttribute(&wt.num_sms, cudaDevAttrMultiProcessorCount, ctx->device) != cudaSuccess) wt.num_sms = 148;
     auto split = [&](const float* w, size_t n, SplitW& s) -> bool {
         void *hi = nullptr, *lo = nullptr;
         if (split_weights(w, n, &hi, &lo) != cudaSuccess) { ctx->err = "cuda: weight split failed"; return false; }
@@ -382,7 +381,7 @@ int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launc
     *launches += launch_features_c2(b, ctx->stream, ctx->kt);
     for (uint64_t n0 = 0; n0 < n_sup; n0 += ctx->chunk_pos) {
         const uint32_t np = (uint32_t)std::min<uint64_t>(ctx->chunk_pos, n_sup - n0);
-        *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, ctx->d_ws.as<float>(), ctx->d_logits.as<float>(),
+        *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, ctx->d_ws.as<uint8_t>(), ctx->d_logits.as<float>(),
                                           ctx->d_info.as<float>(), ctx->stream, ctx->kt);
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -446,7 +445,7 @@ int run_batch(hb_ctx* ctx) {
     CK(ctx->d_fwd_row.ensure(std::max<uint64_t>(n_sup, 1) * 4));
     CK(ctx->d_logits.ensure(std::max<uint64_t>(n_sup, 1) * 5 * 4));
     CK(ctx->d_info.ensure(std::max<uint64_t>(n_sup, 1) * 4));
-    CK(ctx->d_ws.ensure(fwd_workspace_floats(ctx->wt, ctx->chunk_pos) * 4));
+    CK(ctx->d_ws.ensure(fwd_workspace_bytes(ctx->wt, ctx->chunk_pos)));
     b = make_view(ctx, hbt);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     rc = launch_tail(ctx, b, n_sup, &launches);
@@ -888,7 +887,7 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
 
 int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int act, int res, uint32_t lda_extra,
                      float* max_abs_err, float* max_abs_ref, float* ms_tc, float* ms_simt) {
-    if (!max_abs_err || !max_abs_ref || M % 128 || N % 64 || K % 64) return HB_ERR_ARG;
+    if (!max_abs_err || !max_abs_ref || M % 128 || N % 128 || K % 64 || (res && act)) return HB_ERR_ARG;
     if (cudaSetDevice(cuda_device) != cudaSuccess) return HB_ERR_CUDA;
     const size_t lda = (size_t)K + lda_extra;
     std::vector<float> hA((size_t)M * lda), hW((size_t)N * K), hb(N), hR((size_t)M * N);
@@ -909,18 +908,43 @@ int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int ac
     cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dR, hR.data(), hR.size() * 4, cudaMemcpyHostToDevice);
     if (split_weights(dW, hW.size(), &hi, &lo) != cudaSuccess) return HB_ERR_CUDA;
+    void *ahi = nullptr, *alo = nullptr, *ohi = nullptr, *olo = nullptr;
+    if (split_weights(dA, hA.size(), &ahi, &alo) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaMalloc(&ohi, hR.size() * 2) != cudaSuccess || cudaMalloc(&olo, hR.size() * 2) != cudaSuccess) return HB_ERR_CUDA;
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
+    GemmArgs ga{};
+    ga.Ahi = (const __nv_bfloat16*)ahi; ga.Alo = (const __nv_bfloat16*)alo; ga.lda = lda;
+    ga.Whi = (const __nv_bfloat16*)hi; ga.Wlo = (const __nv_bfloat16*)lo; ga.K = K;
+    ga.bias = db; ga.out = dC2; ga.res = res ? dR : nullptr; ga.ldc = N;
+    ga.out_hi = (__nv_bfloat16*)ohi; ga.out_lo = (__nv_bfloat16*)olo; ga.ldo = N;
+    ga.m_tiles = M / 128; ga.n_chunks = N / 128; ga.k_blocks = K / 64;
+    ga.mode = res ? GEMM_OUT_F32_RES : (act == 2 ? GEMM_OUT_SPLIT_RELU : (act ? GEMM_OUT_F32_RELU : GEMM_OUT_F32));
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     cudaError_t e = cudaSuccess;
     for (int rep = 0; rep < 2; rep++) {  // second repetition is the timed one
         cudaEventRecord(e0);
-        gemm_simt(act, res, dA, (int)lda, dW, db, dC1, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
+        gemm_simt(act ? 1 : 0, res, dA, (int)lda, dW, db, dC1, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
         cudaEventRecord(e1);
-        e = gemm_tc(act, res, dA, (int)lda, hi, lo, db, dC2, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
+        e = gemm_tc(ga, num_sms, 0);
         cudaEventRecord(e2);
         if (e != cudaSuccess) break;
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) break;
+    }
+    if (e == cudaSuccess && act == 2) {  // recombine the split output into dC2 for the comparison
+        std::vector<uint16_t> h1(hR.size()), h2(hR.size());
+        cudaMemcpy(h1.data(), ohi, h1.size() * 2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h2.data(), olo, h2.size() * 2, cudaMemcpyDeviceToHost);
+        std::vector<float> c(hR.size());
+        for (size_t i = 0; i < c.size(); i++) {
+            uint32_t a = (uint32_t)h1[i] << 16, b2 = (uint32_t)h2[i] << 16;
+            float fa, fb;
+            memcpy(&fa, &a, 4); memcpy(&fb, &b2, 4);
+            c[i] = fa + fb;
+        }
+        cudaMemcpy(dC2, c.data(), c.size() * 4, cudaMemcpyHostToDevice);
     }
     int rc = HB_OK;
     if (e != cudaSuccess) {
@@ -941,7 +965,7 @@ int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int ac
         if (ms_simt) cudaEventElapsedTime(ms_simt, e0, e1);
         if (ms_tc) cudaEventElapsedTime(ms_tc, e1, e2);
     }
-    cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dR); cudaFree(dC1); cudaFree(dC2); cudaFree(hi); cudaFree(lo);
+    cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dR); cudaFree(dC1); cudaFree(dC2); cudaFree(hi); cudaFree(lo); cudaFree(ahi); cudaFree(alo); cudaFree(ohi); cudaFree(olo);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return rc;
 }

@@ -70,25 +70,47 @@ __global__ void k_stem(BatchView b, FwdWeights wt, uint32_t n0, uint32_t npos, f
     xo[(size_t)31 * C + c] = 0.f;
 }
 
-// ---- LayerNorm over C (eps 1e-5), one warp per token row --------------------------------------
-__global__ void k_layernorm(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ g,
-                            const float* __restrict__ be, uint32_t rows, int C) {
+// ---- LayerNorm over C (eps 1e-5), one warp per token row; output as split bf16 (hi + lo), the
+//      A-operand format of the tcgen05 contractions (gemm_tc.cu) --------------------------------
+__device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void split4(const float (&y)[4], uint2& hi, uint2& lo) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) { h[e] = __float2bfloat16_rn(y[e]); l[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h[e])); }
+    hi = make_uint2(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]));
+    lo = make_uint2(pack_bf2(l[0], l[1]), pack_bf2(l[2], l[3]));
+}
+__global__ void k_layernorm(const float* __restrict__ X, __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo,
+                            const float* __restrict__ g, const float* __restrict__ be, uint32_t rows, int C) {
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* x = X + (size_t)row * C;
     float s = 0.f;
-    for (int i = lane; i < C; i += 32) s += x[i];
+    for (int i = lane * 4; i < C; i += 128) { const float4 v = *(const float4*)(x + i); s += (v.x + v.y) + (v.z + v.w); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(HB_FULL, s, o);
     const float mean = s / (float)C;
-    float v = 0.f;
-    for (int i = lane; i < C; i += 32) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+    float v2 = 0.f;
+    for (int i = lane * 4; i < C; i += 128) {
+        const float4 v = *(const float4*)(x + i);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        v2 = fmaf(a, a, v2); v2 = fmaf(b, b, v2); v2 = fmaf(c, c, v2); v2 = fmaf(d, d, v2);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HB_FULL, v, o);
-    const float rstd = rsqrtf(v / (float)C + 1e-5f);
-    float* y = Y + (size_t)row * C;
-    for (int i = lane; i < C; i += 32) y[i] = (x[i] - mean) * rstd * g[i] + be[i];
+    for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(HB_FULL, v2, o);
+    const float rstd = rsqrtf(v2 / (float)C + 1e-5f);
+    for (int i = lane * 4; i < C; i += 128) {
+        const float4 v = *(const float4*)(x + i), gv = *(const float4*)(g + i), bv = *(const float4*)(be + i);
+        const float y[4] = {(v.x - mean) * rstd * gv.x + bv.x, (v.y - mean) * rstd * gv.y + bv.y,
+                            (v.z - mean) * rstd * gv.z + bv.z, (v.w - mean) * rstd * gv.w + bv.w};
+        uint2 hi, lo;
+        split4(y, hi, lo);
+        *(uint2*)(Yhi + (size_t)row * C + i) = hi;
+        *(uint2*)(Ylo + (size_t)row * C + i) = lo;
+    }
 }
 
 // ---- fp32 GEMM  Cout[M,N] = act(A[M,K] * Wt[N,K]^T + bias) (+ Res) -----------------------------
@@ -150,8 +172,8 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int l
 // ---- read-axis multi-head attention: S = 31 tokens per position ----------------------------
 // one warp per (position, head); lane = query token; online softmax, all in registers.
 template <int DH>
-__global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, float* __restrict__ O, uint32_t npos,
-                                                   int C, int H) {
+__global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, __nv_bfloat16* __restrict__ Ohi,
+                                                   __nv_bfloat16* __restrict__ Olo, uint32_t npos, int C, int H) {
     __shared__ float sK[4][32][DH + 1], sV[4][32][DH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * 4 + warp;
@@ -182,14 +204,15 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV
         for (int d = 0; d < DH; d++) o[d] = fmaf(p, sV[warp][j][d], o[d] * corr);
         m = mn;
     }
-    const float inv = 1.f / l;
-    float* out = O + ((size_t)n * TOK_PER_POS + lane) * C + h * DH;
-    if (lane < R_COLS) {
+    const float inv = (lane < R_COLS) ? 1.f / l : 0.f;  // the pad token row is written as zeros
+    const size_t ob = ((size_t)n * TOK_PER_POS + lane) * C + h * DH;
 #pragma unroll
-        for (int d = 0; d < DH; d++) out[d] = o[d] * inv;
-    } else {
-#pragma unroll
-        for (int d = 0; d < DH; d++) out[d] = 0.f;
+    for (int d = 0; d < DH; d += 4) {
+        const float y[4] = {o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv};
+        uint2 hi, lo;
+        split4(y, hi, lo);
+        *(uint2*)(Ohi + ob + d) = hi;
+        *(uint2*)(Olo + ob + d) = lo;
     }
 }
 
@@ -232,11 +255,28 @@ __global__ void k_heads(BatchView b, FwdWeights wt, uint32_t n0, uint32_t npos, 
 }
 
 // ------------------------------------------------------------------------------------------
-size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos) {
-    const size_t np = (size_t)(chunk_pos + 127) / 128 * 128;  // positions padded to a GEMM tile
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct FwdWs {
+    float *X, *QKV, *Z;
+    __nv_bfloat16 *Hhi, *Hlo, *Fhi, *Flo;
+    size_t bytes;
+};
+static FwdWs carve(const FwdWeights& wt, size_t npos, uint8_t* base) {
+    const size_t np = (npos + 127) / 128 * 128;  // positions padded to a GEMM tile
     const size_t T = np * TOK_PER_POS;
-    return T * (size_t)(wt.C /*X*/ + wt.C /*H*/ + 3 * wt.C /*QKV*/ + wt.F /*F1*/) + np * wt.D /*Z*/;
+    FwdWs w;
+    size_t o = 0;
+    w.X = (float*)(base + o); o += al256(T * wt.C * 4);
+    w.QKV = (float*)(base + o); o += al256(T * 3 * wt.C * 4);
+    w.Z = (float*)(base + o); o += al256(np * wt.D * 4);
+    w.Hhi = (__nv_bfloat16*)(base + o); o += al256(T * wt.C * 2);
+    w.Hlo = (__nv_bfloat16*)(base + o); o += al256(T * wt.C * 2);
+    w.Fhi = (__nv_bfloat16*)(base + o); o += al256(T * wt.F * 2);
+    w.Flo = (__nv_bfloat16*)(base + o); o += al256(T * wt.F * 2);
+    w.bytes = o;
+    return w;
 }
+size_t fwd_workspace_bytes(const FwdWeights& wt, uint32_t chunk_pos) { return carve(wt, chunk_pos, nullptr).bytes; }
 
 void gemm_simt(int act, int res, const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc,
                const float* Res, size_t M, int N, int K, cudaStream_t st) {
@@ -246,12 +286,17 @@ void gemm_simt(int act, int res, const float* A, int lda, const float* Wt, const
     else k_gemm<0, 1><<<grid, 256, 0, st>>>(A, lda, Wt, bias, Cout, ldc, Res, K);
 }
 
-template <int ACT, int RES>
-static void gemm(const FwdWeights& wt, const float* A, int lda, const float* Wt, const SplitW& sw, const float* bias,
-                 float* Cout, int ldc, const float* Res, size_t M, int N, int K, cudaStream_t st, KTimer& kt) {
+static void gemm(const FwdWeights& wt, int mode, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, size_t lda, const SplitW& sw,
+                 const float* bias, float* out, const float* res, size_t ldc, __nv_bfloat16* ohi, __nv_bfloat16* olo, size_t ldo,
+                 size_t M, int N, int K, cudaStream_t st, KTimer& kt) {
+    GemmArgs a{};
+    a.Ahi = Ahi; a.Alo = Alo; a.lda = lda;
+    a.Whi = (const __nv_bfloat16*)sw.hi; a.Wlo = (const __nv_bfloat16*)sw.lo; a.K = (uint32_t)K;
+    a.bias = bias; a.out = out; a.res = res; a.ldc = ldc; a.out_hi = ohi; a.out_lo = olo; a.ldo = ldo;
+    a.m_tiles = (uint32_t)(M / 128); a.n_chunks = (uint32_t)(N / 128); a.k_blocks = (uint32_t)(K / 64);
+    a.mode = mode;
     kt.begin(K_GEMM);
-    if (wt.use_tc && sw.hi) gemm_tc(ACT, RES, A, lda, sw.hi, sw.lo, bias, Cout, ldc, Res, M, N, K, st);
-    else gemm_simt(ACT, RES, A, lda, Wt, bias, Cout, ldc, Res, M, N, K, st);
+    gemm_tc(a, wt.num_sms, st);
     kt.end();
 }
 
@@ -269,42 +314,40 @@ uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops) {
 }
 
 // Runs positions [n0, n0+npos) of the work list.  Returns the number of kernel launches.
-int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, float* ws,
+int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, uint8_t* wsb,
                          float* logits, float* info, cudaStream_t st, KTimer& kt) {
     const int C = wt.C, F = wt.F, D = wt.D, H = wt.H;
     const size_t np_pad = (size_t)(npos + 127) / 128 * 128;
     const size_t T = np_pad * TOK_PER_POS;
-    float* X = ws;
-    float* Hn = X + T * C;
-    float* QKV = Hn + T * C;
-    float* F1 = QKV + T * 3 * C;
-    float* Z = F1 + T * F;
+    const FwdWs ws = carve(wt, npos, wsb);
     int nl = 0;
     // tokens of the pad positions of the last tile must be finite
     if (T > (size_t)npos * TOK_PER_POS)
-        cudaMemsetAsync(X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
+        cudaMemsetAsync(ws.X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
     const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
-    kt.begin(K_STEM); k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, X); kt.end(); nl++;
+    kt.begin(K_STEM); k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, ws.X); kt.end(); nl++;
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
-        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); kt.end(); nl++;
-        gemm<0, 0>(wt, Hn, C, ly.wqkv, ly.s_qkv, ly.bqkv, QKV, 3 * C, nullptr, T, 3 * C, C, st, kt); nl++;
-        const unsigned ab = (unsigned)(((size_t)npos * H + 3) / 4);
+        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); kt.end(); nl++;
+        gemm(wt, GEMM_OUT_F32, ws.Hhi, ws.Hlo, C, ly.s_qkv, ly.bqkv, ws.QKV, nullptr, 3 * C, nullptr, nullptr, 0, T, 3 * C, C, st, kt); nl++;
+        // attention writes its (split) output over the LN buffers: the QKV contraction has consumed them (stream order)
+        const unsigned ab = (unsigned)(((size_t)np_pad * H + 3) / 4);
         kt.begin(K_ATTENTION);
-        if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);
-        else k_attention<32><<<ab, 128, 0, st>>>(QKV, Hn, npos, C, H);  // head_dim validated at load: 16 or 32
+        if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);
+        else k_attention<32><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);  // head_dim validated at load
         kt.end(); nl++;
-        gemm<0, 1>(wt, Hn, C, ly.wo, ly.s_o, ly.bo, X, C, X, T, C, C, st, kt); nl++;
-        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
-        gemm<1, 0>(wt, Hn, C, ly.w1, ly.s_1, ly.b1, F1, F, nullptr, T, F, C, st, kt); nl++;
-        gemm<0, 1>(wt, F1, F, ly.w2, ly.s_2, ly.b2, X, C, X, T, C, F, st, kt); nl++;
+        gemm(wt, GEMM_OUT_F32_RES, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, C, st, kt); nl++;
+        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
+        gemm(wt, GEMM_OUT_SPLIT_RELU, ws.Hhi, ws.Hlo, C, ly.s_1, ly.b1, nullptr, nullptr, 0, ws.Fhi, ws.Flo, F, T, F, C, st, kt); nl++;
+        gemm(wt, GEMM_OUT_F32_RES, ws.Fhi, ws.Flo, F, ly.s_2, ly.b2, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, F, st, kt); nl++;
     }
-    kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(X, Hn, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); kt.end(); nl++;
-    // read-axis collapse: row n = the 31*C contiguous floats of position n (token 31 excluded)
-    gemm<1, 0>(wt, Hn, TOK_PER_POS * C, wt.wc, wt.s_c, wt.bc, Z, D, nullptr, np_pad, D, R_COLS * C, st, kt); nl++;
+    kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); kt.end(); nl++;
+    // read-axis collapse: row n = the 31*C contiguous values of position n (token 31 excluded)
+    gemm(wt, GEMM_OUT_F32_RELU, ws.Hhi, ws.Hlo, (size_t)TOK_PER_POS * C, wt.s_c, wt.bc, ws.Z, nullptr, D, nullptr, nullptr, 0, np_pad, D,
+         R_COLS * C, st, kt); nl++;
     kt.begin(K_HEADS);
-    k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, Z, logits, info);
+    k_heads<<<(unsigned)(((size_t)npos * 32 + 127) / 128), 128, 0, st>>>(b, wt, n0, npos, ws.Z, logits, info);
     kt.end(); nl++;
     return nl;
 }

@@ -1,6 +1,7 @@
 // forward.h — device-resident weights of the forward stage (see herro_b200/weights.py for the
 // blob format and tensor names).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
@@ -28,14 +29,28 @@ struct FwdWeights {
     FwdLayer layer[MAX_LAYERS];
     const float *lnf_g, *lnf_b, *wc, *bc, *wb, *bb, *wi, *bi;
     SplitW s_c;
-    int use_tc;  // 1: tcgen05 bf16x3 contractions (default), 0: fp32 SIMT (HERRO_B200_GEMM=simt)
+    int num_sms;
 };
 
 // gemm_tc.cu
+enum { GEMM_OUT_F32 = 0, GEMM_OUT_F32_RELU = 1, GEMM_OUT_F32_RES = 2, GEMM_OUT_SPLIT_RELU = 3 };
+struct GemmArgs {
+    const __nv_bfloat16 *Ahi, *Alo;  // activations, split bf16, row stride lda (elements)
+    size_t lda;
+    const __nv_bfloat16 *Whi, *Wlo;  // weights [N,K], split bf16
+    uint32_t K;
+    const float* bias;               // [N]
+    float* out;                      // fp32 output (modes F32*), row stride ldc
+    const float* res;                // residual (mode F32_RES), same layout as out
+    size_t ldc;
+    __nv_bfloat16 *out_hi, *out_lo;  // split bf16 output (mode SPLIT_RELU), row stride ldo
+    size_t ldo;
+    uint32_t m_tiles, n_chunks, k_blocks;  // M/128, N/128, K/64
+    int mode;
+};
 cudaError_t split_weights(const float* w, size_t n, void** hi, void** lo);
-cudaError_t gemm_tc(int act, int res, const float* A, int lda, const void* Whi, const void* Wlo, const float* bias, float* Cout,
-                    int ldc, const float* Res, size_t M, int N, int K, cudaStream_t st);
-// forward.cu (fp32 SIMT reference contraction, also used by the self test)
+cudaError_t gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st);
+// forward.cu (fp32 SIMT contraction: the self test's reference)
 void gemm_simt(int act, int res, const float* A, int lda, const float* Wt, const float* bias, float* Cout, int ldc,
                const float* Res, size_t M, int N, int K, cudaStream_t st);
 
@@ -76,8 +91,8 @@ struct KTimer {
 enum { K_TOKENIZE = 0, K_PASS1, K_SCORES, K_PASS2A, K_SCAN, K_PILEUP, K_LISTS, K_STEM, K_LAYERNORM, K_GEMM, K_ATTENTION,
        K_HEADS, K_CONSENSUS };
 
-size_t fwd_workspace_floats(const FwdWeights& wt, uint32_t chunk_pos);
-int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, float* ws,
+size_t fwd_workspace_bytes(const FwdWeights& wt, uint32_t chunk_pos);
+int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, uint8_t* ws,
                          float* logits, float* info, cudaStream_t st, KTimer& kt);
 uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops);
 

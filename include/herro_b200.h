@@ -160,8 +160,9 @@ int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms);
 
 /* ---- diagnostics ------------------------------------------------------------------------- */
 /* Runs the tcgen05 (bf16x3) contraction kernel and the fp32 SIMT one on the same random
- * [M,K]x[N,K]^T problem (M % 128 == 0, N % 64 == 0, K % 64 == 0; lda = K + lda_extra) and
- * reports the largest absolute difference, the largest |reference| and both kernel times. */
+ * [M,K]x[N,K]^T problem (M % 128 == 0, N % 128 == 0, K % 64 == 0; lda = K + lda_extra; act: 0 none,
+ * 1 ReLU, 2 ReLU with split-bf16 output; res: add a residual) and reports the largest absolute
+ * difference, the largest |reference| and both kernel times. */
 int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int act, int res, uint32_t lda_extra,
                      float* max_abs_err, float* max_abs_ref, float* ms_tc, float* ms_simt);
 

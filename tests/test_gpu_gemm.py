@@ -7,13 +7,13 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [  # M, N, K, act, res, lda_extra  — the shapes the forward uses (C=128, F=512, D=256) and edge cases
     (128, 128, 64, 0, 0, 0),
-    (128, 64, 64, 0, 0, 0),
     (256, 384, 128, 0, 0, 0),      # QKV
     (1024, 128, 128, 0, 1, 0),     # out-proj + residual
-    (1024, 512, 128, 1, 0, 0),     # FFN1 + ReLU
+    (1024, 512, 128, 2, 0, 0),     # FFN1 + ReLU, split-bf16 output
     (1024, 128, 512, 0, 1, 0),     # FFN2 + residual
     (256, 256, 3968, 1, 0, 128),   # read-axis collapse, lda = 32*C
-    (384, 192, 192, 0, 0, 64),     # BN=64 path, odd sizes
+    (384, 256, 192, 0, 0, 64),     # odd sizes, padded lda
+    (128 * 301, 384, 128, 0, 0, 0),  # more work items than SMs: persistent loop, ring wrap-around
 ]
 
 
