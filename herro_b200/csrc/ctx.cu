@@ -10,8 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -26,6 +28,7 @@ using namespace hb;
 namespace {
 
 thread_local std::string g_create_err;
+thread_local std::string* t_err_sink = nullptr;  // the launch worker reports into its own string
 
 struct DevBuf {
     void* p = nullptr;
@@ -128,21 +131,33 @@ struct hb_ctx {
     hb_stats stats{};
     LastLaunch last;
     KTimer kt;
+
+    // launch worker: batches are processed asynchronously so that the host can stage batch i+1
+    // (and drain results of batch i-1) while batch i is on the GPU
+    std::thread worker;
+    std::condition_variable cv_work, cv_idle;
+    std::deque<HostBatch> queue;
+    bool stop = false, busy = false;
+    int worker_rc = HB_OK;
+    std::string worker_err;
+    bool idle() const { return queue.empty() && !busy; }
 };
 
 namespace {
+
+std::string& errref(hb_ctx* ctx) { return t_err_sink ? *t_err_sink : ctx->err; }
 
 #define CK(call)                                                                      \
     do {                                                                              \
         cudaError_t e__ = (call);                                                     \
         if (e__ != cudaSuccess) {                                                     \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);           \
+            errref(ctx) = std::string(#call) + ": " + cudaGetErrorString(e__);        \
             return HB_ERR_CUDA;                                                       \
         }                                                                             \
     } while (0)
 
 int fail(hb_ctx* ctx, int code, const std::string& msg) {
-    ctx->err = msg;
+    errref(ctx) = msg;
     return code;
 }
 
@@ -390,9 +405,10 @@ int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launc
     return HB_OK;
 }
 
-int run_batch(hb_ctx* ctx) {
-    HostBatch& hbt = ctx->hbatch;
+int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     if (hbt.tgt.empty()) return HB_OK;
+    hb_stats S{};  // merged into ctx->stats under the lock at the end
+    std::vector<Result> out_results;
     const uint32_t W = ctx->opt.window_size;
     int rc = ensure_batch_buffers(ctx, hbt);
     if (rc) return rc;
@@ -411,7 +427,7 @@ int run_batch(hb_ctx* ctx) {
     void* dst[5] = {ctx->d_tgt.p, ctx->d_win.p, ctx->d_ovl.p, ctx->d_ow.p, ctx->d_cig.p};
     for (int i = 0; i < 5; i++)
         if (sz[i]) CK(cudaMemcpyAsync(dst[i], pin + off[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
+    S.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
 
     if (ctx->rows_cap == 0) { rc = ensure_row_buffers(ctx, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
     CK(ctx->pin_small.ensure(CNT_N * 4 + nw * 4 * 4 + nt * 4 + nw * TOP_K * 4 + 1024));
@@ -470,20 +486,20 @@ int run_batch(hb_ctx* ctx) {
     CK(ctx->pin_out.ensure(total_out + 16));
     if (total_out) CK(cudaMemcpyAsync(ctx->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
+    S.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
 
     // ---- timing
     float ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); ctx->stats.ms_features += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_forward += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->stats.ms_consensus += ms;
-    ctx->kt.collect(ctx->stats.ms_kernel, ctx->stats.n_kernel);
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); S.ms_features += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); S.ms_forward += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); S.ms_consensus += ms;
+    ctx->kt.collect(S.ms_kernel, S.n_kernel);
     ctx->kt.on = false;
     {
         uint64_t gf = 0;
         const uint64_t ff = forward_flops_per_pos(ctx->wt, &gf);
-        ctx->stats.forward_flops += ff * n_sup;
-        ctx->stats.gemm_flops += gf * n_sup;
+        S.forward_flops += ff * n_sup;
+        S.gemm_flops += gf * n_sup;
     }
 
     // ---- per-read reassembly (src/consensus.rs:90-111,222-226)
@@ -521,20 +537,20 @@ int run_batch(hb_ctx* ctx) {
         }
         if (r.status != HB_OK) { r.seg_len.clear(); r.seq.clear(); }
         corrected += r.seq.size();
-        ctx->results.push_back(std::move(r));
+        out_results.push_back(std::move(r));
     }
-    ctx->stats.targets += nt;
-    ctx->stats.windows += nw;
-    ctx->stats.overlap_windows += hbt.ow.size();
-    ctx->stats.rows += total_rows;
-    ctx->stats.supported += n_sup;
-    ctx->stats.corrected_bases += corrected;
-    ctx->stats.kernel_launches += launches;
-    ctx->stats.device_launches += 1;
-    ctx->stats.pileup_algo_bytes += algo;
+    S.targets += nt;
+    S.windows += nw;
+    S.overlap_windows += hbt.ow.size();
+    S.rows += total_rows;
+    S.supported += n_sup;
+    S.corrected_bases += corrected;
+    S.kernel_launches += launches;
+    S.device_launches += 1;
+    S.pileup_algo_bytes += algo;
 
-    // ---- keep metadata for the debug taps / replay
-    LastLaunch& ll = ctx->last;
+    // ---- publish: results, counters and the metadata for the debug taps / replay
+    LastLaunch ll;
     ll.valid = true;
     ll.win = hbt.win;
     ll.w_L.assign(h_L, h_L + nw);
@@ -542,21 +558,62 @@ int run_batch(hb_ctx* ctx) {
     ll.w_nsup.assign(h_nsup, h_nsup + nw);
     ll.w_rowbase.resize(nw);
     ll.w_supbase.resize(nw);
-    ll.index.clear();
     uint64_t rb = 0, sb = 0;
     for (size_t w = 0; w < nw; w++) {
         ll.w_rowbase[w] = rb; rb += h_L[w];
         ll.w_supbase[w] = sb; sb += h_nsup[w];
-        ll.index[((uint64_t)hbt.win[w].rid << 32) | hbt.win[w].wid] = (uint32_t)w;
+        if (ctx->opt.flags & HB_FLAG_KEEP_DEBUG) ll.index[((uint64_t)hbt.win[w].rid << 32) | hbt.win[w].wid] = (uint32_t)w;
     }
     ll.n_sup = n_sup;
     ll.total_rows = total_rows;
     ll.view = b;
-    hbt.clear();
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        hb_stats& T = ctx->stats;
+        T.targets += S.targets; T.windows += S.windows; T.overlap_windows += S.overlap_windows; T.rows += S.rows;
+        T.supported += S.supported; T.corrected_bases += S.corrected_bases; T.h2d_bytes += S.h2d_bytes;
+        T.d2h_bytes += S.d2h_bytes; T.kernel_launches += S.kernel_launches; T.device_launches += S.device_launches;
+        T.pileup_algo_bytes += S.pileup_algo_bytes; T.gemm_flops += S.gemm_flops; T.forward_flops += S.forward_flops;
+        T.ms_features += S.ms_features; T.ms_forward += S.ms_forward; T.ms_consensus += S.ms_consensus;
+        for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) { T.ms_kernel[i] += S.ms_kernel[i]; T.n_kernel[i] += S.n_kernel[i]; }
+        for (auto& r : out_results) ctx->results.push_back(std::move(r));
+        ctx->last = std::move(ll);
+    }
     return HB_OK;
 }
 
-int append_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
+void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk) {
+    if (ctx->hbatch.tgt.empty()) return;
+    ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });  // back-pressure: at most 2 staged batches
+    ctx->queue.push_back(std::move(ctx->hbatch));
+    ctx->hbatch = HostBatch();
+    ctx->cv_work.notify_one();
+}
+
+void worker_main(hb_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    t_err_sink = &ctx->worker_err;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    for (;;) {
+        ctx->cv_work.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
+        if (ctx->queue.empty()) break;  // stop requested and nothing left
+        HostBatch hbt = std::move(ctx->queue.front());
+        ctx->queue.pop_front();
+        ctx->busy = true;
+        ctx->cv_idle.notify_all();
+        lk.unlock();
+        const int rc = run_batch(ctx, hbt);
+        lk.lock();
+        if (rc != HB_OK) {
+            if (ctx->worker_rc == HB_OK) ctx->worker_rc = rc;
+            for (const auto& t : hbt.tgt) ctx->results.push_back(Result{t.rid, rc, {}, {}});
+        }
+        ctx->busy = false;
+        ctx->cv_idle.notify_all();
+    }
+}
+
+int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
                   const hb_overlap_window* ow, uint32_t n_ow) {
     if (!ctx->have_reads) return fail(ctx, HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
     if (rid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "rid out of range");
@@ -609,7 +666,7 @@ int append_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overla
         hbt.op_cap += (d.cei - d.csi) / 2 + 1;
     }
     hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl});
-    if (hbt.tgt.size() >= ctx->opt.launch_targets) return run_batch(ctx);
+    if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk);
     return HB_OK;
 }
 
@@ -652,12 +709,21 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
     int rc = load_weights(ctx, model_path);
     if (rc) return bail(rc);
+    ctx->worker = std::thread(worker_main, ctx);
     *out = ctx;
     return HB_OK;
 }
 
 void hb_destroy(hb_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->worker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->stop = true;
+        }
+        ctx->cv_work.notify_all();
+        ctx->worker.join();
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->weight_allocs) cudaFree(p);
@@ -681,7 +747,9 @@ void hb_destroy(hb_ctx* ctx) {
 int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_words, const uint32_t* seq_len,
                     const uint8_t* const* qual) {
     if (!ctx) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
+    if (!ctx->hbatch.tgt.empty()) return fail(ctx, HB_ERR_STATE, "hb_upload_reads with targets pending: call hb_flush first");
     if (!seq_words || !seq_len || !qual || n_reads == 0) return fail(ctx, HB_ERR_ARG, "null/empty read store");
     CK(cudaSetDevice(ctx->device));
     std::vector<uint64_t> woff(n_reads + 1, 0), qoff(n_reads + 1, 0);
@@ -747,9 +815,8 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
 int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
                      const hb_overlap_window* ow, uint32_t n_ow) {
     if (!ctx) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
-    return append_target(ctx, rid, n_windows, ovl, n_ovl, ow, n_ow);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ow, n_ow);
 }
 
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl) {
@@ -765,9 +832,8 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
         if (host_extract_windows(ovl[i], i, W, n_windows, ows) != 0)
             return fail(ctx, HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
-    return append_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
 }
 
 int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
@@ -783,9 +849,12 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
 
 int hb_flush(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HB_ERR_CUDA, "cudaSetDevice");
-    return run_batch(ctx);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    enqueue_current(ctx, lk);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
+    const int rc = ctx->worker_rc;
+    if (rc != HB_OK) { ctx->err = ctx->worker_err; ctx->worker_rc = HB_OK; }
+    return rc;
 }
 
 int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg_len, uint32_t* n_segs) {
@@ -843,7 +912,8 @@ static int find_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* w) {
 
 int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* shape4) {
     if (!ctx || !shape4) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     uint32_t w;
     int rc = find_window(ctx, rid, wid, &w);
     if (rc) return rc;
@@ -857,7 +927,8 @@ int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* sha
 int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases, uint8_t* quals, uint32_t* supported,
                          uint32_t* sup_rows, float* info_logits, float* bases_logits) {
     if (!ctx) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     CK(cudaSetDevice(ctx->device));
     uint32_t w;
     int rc = find_window(ctx, rid, wid, &w);
@@ -972,7 +1043,8 @@ int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int ac
 
 int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {
     if (!ctx || !ms) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     CK(cudaSetDevice(ctx->device));
     if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch to replay");
     const BatchView b = ctx->last.view;

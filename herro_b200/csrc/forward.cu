@@ -174,34 +174,46 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int l
 template <int DH>
 __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, __nv_bfloat16* __restrict__ Ohi,
                                                    __nv_bfloat16* __restrict__ Olo, uint32_t npos, int C, int H) {
-    __shared__ float sK[4][32][DH + 1], sV[4][32][DH + 1];
+    __shared__ __align__(16) float sK[4][32][DH + 4], sV[4][32][DH + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * 4 + warp;
     if (item >= npos * (uint32_t)H) return;
     const uint32_t n = item / H, h = item % H;
     const float* base = QKV + (size_t)n * TOK_PER_POS * 3 * C;
-    // stage K and V of this head: 32 tokens x DH
-    for (int i = lane; i < 32 * DH; i += 32) {
-        const int t = i / DH, d = i % DH;
-        sK[warp][t][d] = base[(size_t)t * 3 * C + C + h * DH + d];
-        sV[warp][t][d] = base[(size_t)t * 3 * C + 2 * C + h * DH + d];
+    // stage K and V of this head: 32 tokens x DH, 16-byte loads (a row of a head is DH*4 contiguous bytes)
+    constexpr int V4 = DH / 4;
+    for (int i = lane; i < 32 * V4; i += 32) {
+        const int t = i / V4, d4 = (i % V4) * 4;
+        *(float4*)&sK[warp][t][d4] = *(const float4*)(base + (size_t)t * 3 * C + C + h * DH + d4);
+        *(float4*)&sV[warp][t][d4] = *(const float4*)(base + (size_t)t * 3 * C + 2 * C + h * DH + d4);
     }
     float q[DH], o[DH];
 #pragma unroll
-    for (int d = 0; d < DH; d++) { q[d] = base[(size_t)lane * 3 * C + h * DH + d]; o[d] = 0.f; }
+    for (int d = 0; d < DH; d += 4) {
+        const float4 v = *(const float4*)(base + (size_t)lane * 3 * C + h * DH + d);
+        q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
+        o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+    }
     __syncwarp();
     const float scale = rsqrtf((float)DH);
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < R_COLS; j++) {
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int d = 0; d < DH; d++) s = fmaf(q[d], sK[warp][j][d], s);
-        s *= scale;
+        for (int d = 0; d < DH; d += 4) {
+            const float4 k = *(const float4*)&sK[warp][j][d];
+            s0 = fmaf(q[d], k.x, s0); s1 = fmaf(q[d + 1], k.y, s1); s2 = fmaf(q[d + 2], k.z, s2); s3 = fmaf(q[d + 3], k.w, s3);
+        }
+        const float s = ((s0 + s1) + (s2 + s3)) * scale;
         const float mn = fmaxf(m, s);
         const float corr = expf(m - mn), p = expf(s - mn);
         l = l * corr + p;
 #pragma unroll
-        for (int d = 0; d < DH; d++) o[d] = fmaf(p, sV[warp][j][d], o[d] * corr);
+        for (int d = 0; d < DH; d += 4) {
+            const float4 v = *(const float4*)&sV[warp][j][d];
+            o[d] = fmaf(p, v.x, o[d] * corr); o[d + 1] = fmaf(p, v.y, o[d + 1] * corr);
+            o[d + 2] = fmaf(p, v.z, o[d + 2] * corr); o[d + 3] = fmaf(p, v.w, o[d + 3] * corr);
+        }
         m = mn;
     }
     const float inv = (lane < R_COLS) ? 1.f / l : 0.f;  // the pad token row is written as zeros
@@ -300,6 +312,22 @@ static void gemm(const FwdWeights& wt, int mode, const __nv_bfloat16* Ahi, const
     kt.end();
 }
 
+// residual-stream contraction with N == C == 128 and the following LayerNorm fused in the epilogue
+static void gemm_ln(const FwdWeights& wt, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, size_t lda, const SplitW& sw,
+                    const float* bias, float* X, const float* ln_g, const float* ln_b, __nv_bfloat16* ohi, __nv_bfloat16* olo,
+                    size_t M, int K, cudaStream_t st, KTimer& kt) {
+    GemmArgs a{};
+    a.Ahi = Ahi; a.Alo = Alo; a.lda = lda;
+    a.Whi = (const __nv_bfloat16*)sw.hi; a.Wlo = (const __nv_bfloat16*)sw.lo; a.K = (uint32_t)K;
+    a.bias = bias; a.out = X; a.res = X; a.ldc = 128; a.out_hi = ohi; a.out_lo = olo; a.ldo = 128;
+    a.ln_g = ln_g; a.ln_b = ln_b;
+    a.m_tiles = (uint32_t)(M / 128); a.n_chunks = 1; a.k_blocks = (uint32_t)(K / 64);
+    a.mode = GEMM_OUT_F32_RES_LN;
+    kt.begin(K_GEMM);
+    gemm_tc(a, wt.num_sms, st);
+    kt.end();
+}
+
 // algorithmic FLOPs per supported position (2 * MACs), and the part that is dense contractions
 uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops) {
     const uint64_t C = wt.C, F = wt.F, D = wt.D, K = wt.stem_k, S = R_COLS, dh = wt.C / wt.H;
@@ -327,9 +355,14 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
     kt.begin(K_STEM); k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, ws.X); kt.end(); nl++;
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
+    // With C == 128 a contraction that writes the residual stream owns whole rows in its epilogue, so the
+    // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
+    const bool fuse_ln = (C == 128);
+    kt.begin(K_LAYERNORM);
+    k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
+    kt.end(); nl++;
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
-        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln1_g, ly.ln1_b, (uint32_t)T, C); kt.end(); nl++;
         gemm(wt, GEMM_OUT_F32, ws.Hhi, ws.Hlo, C, ly.s_qkv, ly.bqkv, ws.QKV, nullptr, 3 * C, nullptr, nullptr, 0, T, 3 * C, C, st, kt); nl++;
         // attention writes its (split) output over the LN buffers: the QKV contraction has consumed them (stream order)
         const unsigned ab = (unsigned)(((size_t)np_pad * H + 3) / 4);
@@ -337,12 +370,24 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
         if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);
         else k_attention<32><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);  // head_dim validated at load
         kt.end(); nl++;
-        gemm(wt, GEMM_OUT_F32_RES, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, C, st, kt); nl++;
-        kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
+        // out-proj + residual (+ LN2 -> split H).  In-place on H is safe: a row's outputs are written by the
+        // thread that owns the row only after every MMA that reads the tile has completed (tfull barrier).
+        if (fuse_ln) {
+            gemm_ln(wt, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ly.ln2_g, ly.ln2_b, ws.Hhi, ws.Hlo, T, C, st, kt); nl++;
+        } else {
+            gemm(wt, GEMM_OUT_F32_RES, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, C, st, kt); nl++;
+            kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
+        }
         gemm(wt, GEMM_OUT_SPLIT_RELU, ws.Hhi, ws.Hlo, C, ly.s_1, ly.b1, nullptr, nullptr, 0, ws.Fhi, ws.Flo, F, T, F, C, st, kt); nl++;
-        gemm(wt, GEMM_OUT_F32_RES, ws.Fhi, ws.Flo, F, ly.s_2, ly.b2, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, F, st, kt); nl++;
+        const float* ng = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_g : wt.lnf_g;
+        const float* nb = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_b : wt.lnf_b;
+        if (fuse_ln) {
+            gemm_ln(wt, ws.Fhi, ws.Flo, F, ly.s_2, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo, T, F, st, kt); nl++;
+        } else {
+            gemm(wt, GEMM_OUT_F32_RES, ws.Fhi, ws.Flo, F, ly.s_2, ly.b2, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, F, st, kt); nl++;
+            kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ng, nb, (uint32_t)T, C); kt.end(); nl++;
+        }
     }
-    kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.lnf_g, wt.lnf_b, (uint32_t)T, C); kt.end(); nl++;
     // read-axis collapse: row n = the 31*C contiguous values of position n (token 31 excluded)
     gemm(wt, GEMM_OUT_F32_RELU, ws.Hhi, ws.Hlo, (size_t)TOK_PER_POS * C, wt.s_c, wt.bc, ws.Z, nullptr, D, nullptr, nullptr, 0, np_pad, D,
          R_COLS * C, st, kt); nl++;

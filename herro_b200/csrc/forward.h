@@ -33,7 +33,8 @@ struct FwdWeights {
 };
 
 // gemm_tc.cu
-enum { GEMM_OUT_F32 = 0, GEMM_OUT_F32_RELU = 1, GEMM_OUT_F32_RES = 2, GEMM_OUT_SPLIT_RELU = 3 };
+enum { GEMM_OUT_F32 = 0, GEMM_OUT_F32_RELU = 1, GEMM_OUT_F32_RES = 2, GEMM_OUT_SPLIT_RELU = 3,
+       GEMM_OUT_F32_RES_LN = 4 /* N == 128: out = acc+bias+res (fp32) and LayerNorm(out) as split bf16 */ };
 struct GemmArgs {
     const __nv_bfloat16 *Ahi, *Alo;  // activations, split bf16, row stride lda (elements)
     size_t lda;
@@ -45,6 +46,7 @@ struct GemmArgs {
     size_t ldc;
     __nv_bfloat16 *out_hi, *out_lo;  // split bf16 output (mode SPLIT_RELU), row stride ldo
     size_t ldo;
+    const float *ln_g, *ln_b;        // LayerNorm affine (mode F32_RES_LN)
     uint32_t m_tiles, n_chunks, k_blocks;  // M/128, N/128, K/64
     int mode;
 };

@@ -202,6 +202,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const size_t row = (size_t)m0 + warp * 32 + lane;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
+            if (g.mode == GEMM_OUT_F32_RES_LN) {
+                // the thread owns its whole 128-wide row: residual add, fp32 store, LayerNorm, split-bf16 store
+                float x[BN];
+                float* xrow = g.out + row * g.ldc;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = *(const float4*)(g.bias + c0 + j);
+                        const float4 r = *(const float4*)(xrow + c0 + j);
+                        x[c0 + j] = __uint_as_float(v[j]) + bv.x + r.x; x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bv.y + r.y;
+                        x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bv.z + r.z; x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bv.w + r.w;
+                        *(float4*)(xrow + c0 + j) = make_float4(x[c0 + j], x[c0 + j + 1], x[c0 + j + 2], x[c0 + j + 3]);
+                    }
+                }
+                // TMEM is drained: let the MMA warp start the next item while this thread normalises
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&tempty_bar[acc]);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < BN; j++) sum += x[j];
+                const float mean = sum * (1.f / BN);
+                float var = 0.f;
+#pragma unroll
+                for (int j = 0; j < BN; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
+                const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
+                uint4* ph = (uint4*)(g.out_hi + row * g.ldo);
+                uint4* pl = (uint4*)(g.out_lo + row * g.ldo);
+#pragma unroll
+                for (int j = 0; j < BN; j += 8) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const float a = (x[j + e] - mean) * rstd * g.ln_g[j + e] + g.ln_b[j + e];
+                        const float b = (x[j + e + 1] - mean) * rstd * g.ln_g[j + e + 1] + g.ln_b[j + e + 1];
+                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                        hi[e >> 1] = pack2(ah, bh);
+                        lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                    }
+                    ph[j >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    pl[j >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
