@@ -271,6 +271,22 @@ int load_weights(hb_ctx* ctx, const char* path) {
             !split(ly.w1, (size_t)F * C, ly.s_1) || !split(ly.w2, (size_t)C * F, ly.s_2)) return HB_ERR_CUDA;
     }
     if (!split(wt.wc, (size_t)D * 31 * C, wt.s_c)) return HB_ERR_CUDA;
+    // W' of the tensor-core stem: [C][taps*16] = tab (11 token slots), wq twice (q_hi, q_lo columns), zero padding
+    wt.stem_kblocks = 0;
+    if (C == 128 && K <= 64 && !getenv("HERRO_B200_STEM_SIMT")) {
+        const int kbl = (K * 16 + 63) / 64, Kp = kbl * 64;
+        std::vector<float> wp((size_t)C * Kp, 0.f);
+        for (int c = 0; c < C; c++)
+            for (int j = 0; j < K; j++) {
+                for (int t = 0; t < 11; t++) wp[(size_t)c * Kp + j * 16 + t] = tab[((size_t)j * 12 + t) * C + c];
+                wp[(size_t)c * Kp + j * 16 + 11] = wq[(size_t)j * C + c];
+                wp[(size_t)c * Kp + j * 16 + 12] = wq[(size_t)j * C + c];
+            }
+        const float* dwp = nullptr;
+        if (!upload(wp.data(), wp.size(), dwp)) return HB_ERR_CUDA;
+        if (!split(dwp, wp.size(), wt.s_stem)) return HB_ERR_CUDA;
+        wt.stem_kblocks = kbl;
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "cuda: weight split kernel failed"; return HB_ERR_CUDA; }
     return HB_OK;
 }
@@ -958,7 +974,7 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
 
 int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int act, int res, uint32_t lda_extra,
                      float* max_abs_err, float* max_abs_ref, float* ms_tc, float* ms_simt) {
-    if (!max_abs_err || !max_abs_ref || M % 128 || N % 128 || K % 64 || (res && act)) return HB_ERR_ARG;
+    if (!max_abs_err || !max_abs_ref || M % 128 || N % 128 || K % 64 || (res && act && act != 3)) return HB_ERR_ARG;
     if (cudaSetDevice(cuda_device) != cudaSuccess) return HB_ERR_CUDA;
     const size_t lda = (size_t)K + lda_extra;
     std::vector<float> hA((size_t)M * lda), hW((size_t)N * K), hb(N), hR((size_t)M * N);
@@ -991,10 +1007,16 @@ int hb_selftest_gemm(int cuda_device, uint32_t M, uint32_t N, uint32_t K, int ac
     ga.out_hi = (__nv_bfloat16*)ohi; ga.out_lo = (__nv_bfloat16*)olo; ga.ldo = N;
     ga.m_tiles = M / 128; ga.n_chunks = N / 128; ga.k_blocks = K / 64;
     ga.mode = res ? GEMM_OUT_F32_RES : (act == 2 ? GEMM_OUT_SPLIT_RELU : (act ? GEMM_OUT_F32_RELU : GEMM_OUT_F32));
+    if (act == 3) {  // residual + fused LayerNorm epilogue (N must be 128); compares the fp32 residual-stream output
+        if (N != 128) return HB_ERR_ARG;
+        ga.mode = GEMM_OUT_F32_RES_LN; ga.res = dC2; ga.ln_g = db; ga.ln_b = db; res = 1; act = 0;
+        cudaMemcpy(dC2, dR, hR.size() * 4, cudaMemcpyDeviceToDevice);
+    }
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     cudaError_t e = cudaSuccess;
     for (int rep = 0; rep < 2; rep++) {  // second repetition is the timed one
+        if (ga.mode == GEMM_OUT_F32_RES_LN) cudaMemcpy(dC2, dR, hR.size() * 4, cudaMemcpyDeviceToDevice);  // in-place residual
         cudaEventRecord(e0);
         gemm_simt(act ? 1 : 0, res, dA, (int)lda, dW, db, dC1, (int)N, res ? dR : nullptr, M, (int)N, (int)K, 0);
         cudaEventRecord(e1);

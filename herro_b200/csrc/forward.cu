@@ -12,6 +12,8 @@
 // the Lmax of the reference batch, zero beyond; H10) reproduced arithmetically.
 //
 // This is the fp32 SIMT implementation (bit-for-bit order-insensitive to ~1e-6 vs torch fp32).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "forward.h"
 
@@ -353,11 +355,20 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     if (T > (size_t)npos * TOK_PER_POS)
         cudaMemsetAsync(ws.X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
     const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
-    kt.begin(K_STEM); k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, ws.X); kt.end(); nl++;
+    kt.begin(K_STEM);
+    if (wt.stem_kblocks) {
+        StemArgs sa{(const __nv_bfloat16*)wt.s_stem.hi, (const __nv_bfloat16*)wt.s_stem.lo, (uint32_t)wt.stem_kblocks * 64,
+                    (uint32_t)wt.stem_kblocks, (uint32_t)wt.stem_k, wt.stem_b, wt.read_pos, ws.X, n0, npos};
+        stem_tc(b, sa, wt.num_sms, st);
+    } else {
+        k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, ws.X);
+    }
+    kt.end(); nl++;
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
     // With C == 128 a contraction that writes the residual stream owns whole rows in its epilogue, so the
     // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
-    const bool fuse_ln = (C == 128);
+    static const bool fuse_env = getenv("HERRO_B200_FUSE_LN") != nullptr;  // experimental: slower than the separate kernel so far
+    const bool fuse_ln = (C == 128) && fuse_env;
     kt.begin(K_LAYERNORM);
     k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
     kt.end(); nl++;

@@ -29,6 +29,8 @@ struct FwdWeights {
     FwdLayer layer[MAX_LAYERS];
     const float *lnf_g, *lnf_b, *wc, *bc, *wb, *bb, *wi, *bi;
     SplitW s_c;
+    SplitW s_stem;          // W' of the tensor-core stem, [C][stem_kp]
+    int stem_kblocks = 0;   // 0: tensor-core stem unavailable (C != 128 or too many taps)
     int num_sms;
 };
 
@@ -50,6 +52,15 @@ struct GemmArgs {
     uint32_t m_tiles, n_chunks, k_blocks;  // M/128, N/128, K/64
     int mode;
 };
+struct StemArgs {  // k_stem_tc: the stem as a contraction over taps x 16 features (C == 128 only)
+    const __nv_bfloat16 *Whi, *Wlo;  // W' [128][Kp], split bf16
+    uint32_t Kp;                     // k_blocks * 64
+    uint32_t k_blocks, taps;
+    const float *bias, *read_pos;    // [128], [31][128]
+    float* X;                        // [positions*32][128]
+    uint32_t n0, npos;               // work-list range
+};
+cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStream_t st);
 cudaError_t split_weights(const float* w, size_t n, void** hi, void** lo);
 cudaError_t gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st);
 // forward.cu (fp32 SIMT contraction: the self test's reference)

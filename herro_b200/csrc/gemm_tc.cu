@@ -304,6 +304,207 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem on the tensor cores: Embedding(12,6) ++ qual -> Conv(7->C, k=(K,1)) is linear in the one-hot
+// token and in the quality value, so per read token it is a contraction over K' = taps x 16 features
+// (11 one-hot token slots, q_hi, q_lo, 3 zero) with W'[c][j*16+f] = tab[j][f][c] / wq[j][c].  The A
+// operand is exact in bf16 (one-hot entries, and the normalised quality carried as two bf16 columns),
+// so two passes (A.W_hi + A.W_lo) reproduce the fp32 result.  Producers synthesise the swizzled A tile
+// straight from the [L',32] token/quality matrix (pad/zero rows of the reference batch as in k_stem).
+// Same skeleton as k_gemm_ws; one work item = 4 supported positions = 128 read tokens.
+// ------------------------------------------------------------------------------------------------
+constexpr int STEM_STAGE_BYTES = (BM + 2 * BN) * 128;  // A (hi only) + W' hi/lo tiles of one k-block: 48 KB
+constexpr int STEM_MAXK = 64;                           // taps supported by the staging buffers
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArgs g) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t* tokbuf = smem + STAGES * STEM_STAGE_BYTES;          // [2][4 positions][STEM_MAXK taps][32] tokens
+    uint8_t* qbuf = tokbuf + 2 * 4 * STEM_MAXK * 32;             // same shape, raw quality bytes
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t n_items = (g.npos + 3) / 4;
+    const uint32_t kbs = g.k_blocks;
+    const int K = g.taps;
+
+    if (warp >= 4 && warp < 8) {
+        // =============================== producers ===============================
+        const int p = tid - 128;
+        const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
+        uint32_t it_stage = 0, n_done = 0;
+        int pending = -1;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+            // ---- stage the K x 32 token / quality neighbourhood of the 4 positions of this item
+            uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            for (int i = p; i < 4 * K * 2; i += NUM_PROD) {  // one 16-byte half row per iteration
+                const int pos = i / (K * 2), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
+                const uint32_t n = item * 4 + pos;
+                uint4 tv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), qv = make_uint4(0, 0, 0, 0);
+                if (n < g.npos) {
+                    const uint32_t w = b.fwd_win[g.n0 + n], r = b.fwd_row[g.n0 + n];
+                    const uint32_t L = b.w_L[w], Lref = b.w_reflmax[w];
+                    const int64_t row = (int64_t)r + j - K / 2;
+                    if (row >= 0 && row < (int64_t)Lref) {
+                        if (row < (int64_t)L) {
+                            const uint64_t off = (b.w_rowbase[w] + row) * ROW_BYTES + half * 16;
+                            tv = *(const uint4*)(b.mat_bases + off);
+                            qv = *(const uint4*)(b.mat_quals + off);
+                        } else {  // batch padding row of the reference's collate: token 11, qual byte 126
+                            tv = make_uint4(0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu);
+                            qv = make_uint4(0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu);
+                        }
+                    }
+                }
+                *(uint4*)(tb + (pos * STEM_MAXK + j) * 32 + half * 16) = tv;
+                *(uint4*)(qb + (pos * STEM_MAXK + j) * 32 + half * 16) = qv;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // producers only
+            for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
+                const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sA = smem + (size_t)s * STEM_STAGE_BYTES;
+                const uint32_t sb = smem_u32(sA);
+                // ---- W' k-block: 128 rows x 8 chunks, hi and lo
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int idx = i * 128 + p, r = idx >> 3, c = idx & 7;
+                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                    const size_t gw = (size_t)r * g.Kp + (size_t)kb * BK + c * 8;
+                    cp_async16(sb + BM * 128 + off, g.Whi + gw);
+                    cp_async16(sb + BM * 128 + BN * 128 + off, g.Wlo + gw);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                // ---- A k-block: 4 taps x 16 features per row; (row, tap) items, 4 per thread
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int idx = i * 128 + p, r = idx >> 2, tl = idx & 3;  // row 0..127, tap-in-block 0..3
+                    const int j = (int)kb * 4 + tl;
+                    const int pos = r >> 5, rd = r & 31;
+                    uint32_t w16[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 16 bf16 features
+                    if (j < K && rd < R_COLS) {
+                        const uint8_t tok = tb[(pos * STEM_MAXK + j) * 32 + rd];
+                        if (tok != 0xff) {
+                            const uint32_t one = (tok & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0 in the odd / even half
+#pragma unroll
+                            for (int e = 0; e < 6; e++) w16[e] = (tok < 11 && (tok >> 1) == e) ? one : 0u;
+                            const float q = __fsub_rn(__fmul_rn((float)qb[(pos * STEM_MAXK + j) * 32 + rd], QS), QO);
+                            const __nv_bfloat16 qh = __float2bfloat16_rn(q);
+                            const __nv_bfloat16 ql = __float2bfloat16_rn(q - __bfloat162float(qh));
+                            w16[5] |= (uint32_t)__bfloat16_as_ushort(qh) << 16;  // feature 11
+                            w16[6] |= (uint32_t)__bfloat16_as_ushort(ql);        // feature 12
+                        }
+                    }
+                    const int c0 = tl * 2;
+                    *(uint4*)(sA + (uint32_t)r * 128u + (uint32_t)(((c0) ^ (r & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+                    *(uint4*)(sA + (uint32_t)r * 128u + (uint32_t)(((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                }
+                // publish the previous stage (its cp.asyncs have had a stage's worth of time), keep this one pending
+                if (pending >= 0) {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&full_bar[pending]);
+                }
+                pending = (int)s;
+            }
+        }
+        if (pending >= 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[pending]);
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            uint32_t it_stage = 0, n_done = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+                const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
+                    const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sb = smem_u32(smem + (size_t)s * STEM_STAGE_BYTES);
+                    const uint64_t dA = make_desc(sb);
+                    const uint64_t dBh = make_desc(sb + BM * 128), dBl = make_desc(sb + BM * 128 + BN * 128);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        mma_bf16(tmem_d, dA + adv, dBh + adv, (kb | (uint32_t)k) ? 1u : 0u);
+                        mma_bf16(tmem_d, dA + adv, dBl + adv, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // =============================== epilogue: relu(acc + bias) + read_pos ===============================
+        uint32_t n_done = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+            const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const size_t row = (size_t)item * BM + warp * 32 + lane;  // token row: position = item*4 + warp, read = lane
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
+            float* out = g.X + row * BN;
+            const float* rp = g.read_pos + (size_t)(lane < R_COLS ? lane : 0) * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *(const float4*)(g.bias + c0 + j);
+                    const float4 pv = *(const float4*)(rp + c0 + j);
+                    float4 o = make_float4(fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x, fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y,
+                                           fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z, fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w);
+                    if (lane >= R_COLS) o = make_float4(0.f, 0.f, 0.f, 0.f);  // the pad token of every position
+                    *(float4*)(out + c0 + j) = o;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    }
+}
+
+cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)STAGES * STEM_STAGE_BYTES + 2 * 2 * 4 * STEM_MAXK * 32 + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint32_t items = (a.npos + 3) / 4;
+    if (items == 0) return cudaSuccess;
+    k_stem_tc<<<(unsigned)std::min<uint32_t>(items, (uint32_t)num_sms), NUM_THREADS, smem, st>>>(b, a);
+    return cudaGetLastError();
+}
+
 // split fp32 values into bf16 hi / lo (weights at model load; the self test's activations)
 __global__ void k_split_bf16(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
