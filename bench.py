@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--feature-threads", type=int, default=8, help="reference -t: host threads submitting targets")
     return ap.parse_args()
 
 
@@ -208,49 +209,34 @@ def main():
     rs, t_gen = make_readset(args, rank)
     n_steps = args.warmup + args.steps
     lt = min(args.launch_targets, max(1, rs.n // n_steps))
-    # ---- host side that stays in the Rust binary: windowing (timed, outside the measured region)
-    t0 = time.time()
-    ovls, wins, nwin = {}, {}, {}
-    for t in range(n_steps * lt):
-        a0, a1 = int(rs.aln_off[t]), int(rs.aln_off[t + 1])
-        ovls[t] = Context.make_overlaps(rs.ovl9[a0:a1], rs.cigars, rs.cig_off[a0:a1 + 1])
-        nwin[t] = (int(rs.off[t + 1] - rs.off[t]) + args.window - 1) // args.window
-        wins[t] = api.extract_windows(ovls[t], args.window, nwin[t])
-    t_windowing = time.time() - t0
-
     ctx = Context(model, local_rank, args.window, args.batch_size, launch_targets=lt)
     t0 = time.time()
     ctx.upload_reads(rs.seqs, rs.quals, rs.off)
     torch.cuda.synchronize()
     t_upload = time.time() - t0
+    # The C++ host harness plays the Rust binary: `-t` feature threads submit targets through the C ABI,
+    # one consumer thread polls corrected reads (herro_b200/host/harness.cpp).
+    harness = api.HostHarness(ctx, rs.ovl9, rs.cigars, rs.cig_off, rs.aln_off, np.diff(rs.off).astype(np.uint32))
+    nthr = max(1, min(args.feature_threads, threads))
+    # ---- host side that stays in the Rust binary: windowing (timed, outside the measured region)
+    t0 = time.time()
+    win_warm = harness.windowing(0, args.warmup * lt, nthr)
+    win_timed = harness.windowing(args.warmup * lt, n_steps * lt, nthr)
+    t_windowing = time.time() - t0
 
-    def submit_step(s):
-        for t in range(s * lt, (s + 1) * lt):
-            ctx.submit_target(t, nwin[t], ovls[t], wins[t])   # the lt-th submit hands the batch to the launch worker
-
-    def drain():
-        return sum(sum(len(x) for x in r.segments) for r in ctx.drain())
-
-    for s in range(args.warmup):
-        submit_step(s)
-    ctx.flush()
-    drain()
+    harness.run(0, args.warmup * lt, nthr, win_warm)
     ctx.replay_last_launch(1)
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- region 1: end to end through the C ABI, host buffers, copies inside.  Steps are pipelined the way
-    #      the host would run them: batch i+1 is staged while batch i is on the GPU; results are polled as they come.
+    # ---- region 1: end to end through the C ABI, host buffers, copies inside: hb_submit_target from the
+    #      feature threads (batch i+1 is staged while batch i is on the GPU), hb_poll_corrected from the consumer.
     barrier()
     t0 = time.perf_counter()
-    bases_e2e = 0
-    for s in range(args.warmup, n_steps):
-        submit_step(s)
-        bases_e2e += drain()
-    ctx.flush()
-    bases_e2e += drain()
+    r_e2e = harness.run(args.warmup * lt, n_steps * lt, nthr, win_timed)
     barrier()
     t_e2e = time.perf_counter() - t0
+    bases_e2e = r_e2e["bases"]
     st = ctx.stats()
     # ---- region 2: device stages only, inputs resident in HBM (one launch's working set is several
     #      hundred MB of matrices + activations, larger than the 126 MB L2, so no L2 flush is needed)
@@ -302,7 +288,7 @@ def main():
                        "supported_positions_per_step": st["supported"] / max(st["device_launches"], 1),
                        "sharding": "one read cluster per GPU (read-id shard), no collective" if args.gpus > 1 else "single GPU",
                        "l2": "inputs larger than L2 (per-launch working set >> 126 MB)",
-                       "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
+                       "host_feature_threads": nthr, "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
                        "model": {"channels": cfg.channels, "heads": cfg.heads, "layers": cfg.layers, "ffn": cfg.ffn,
                                  "stem_k": cfg.stem_k, "collapse": cfg.collapse, "weights": "random init (no checkpoint offline)"}},
             "e2e": {"value": bases_e2e_all / t_e2e, "unit": UNIT,

@@ -49,6 +49,9 @@ class HbStats(C.Structure):
                [("ms_kernel", C.c_double * 16), ("n_kernel", C.c_uint64 * 16)]
 
 
+HOST_LIB_PATH = os.path.join(_HERE, "libherro_host.so")
+
+
 class HerroError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"herro_b200 error {code}: {msg}")
@@ -286,6 +289,63 @@ class Context:
         ms = C.c_float()
         self._check(self._L.hb_replay_last_launch(self._h, iters, C.byref(ms)))
         return float(ms.value)
+
+
+# ------------------------------------------------------------------------------------------
+# C++ host harness (herro_b200/host/harness.cpp): the Rust binary's thread topology over the C ABI
+# ------------------------------------------------------------------------------------------
+_host = None
+
+
+def _host_lib():
+    global _host
+    if _host is None:
+        load_library()
+        H = C.CDLL(HOST_LIB_PATH)
+        vp, u32 = C.c_void_p, C.c_uint32
+        H.hbh_windowing.argtypes = [vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, C.c_uint64]
+        H.hbh_run.argtypes = [vp, vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, vp, vp, vp]
+        _host = H
+    return _host
+
+
+class HostHarness:
+    """Feature threads + consumer thread over one Context, like src/lib.rs:154-200 for one device."""
+
+    def __init__(self, ctx: "Context", ovl9: np.ndarray, cigars: np.ndarray, cig_off: np.ndarray, aln_off: np.ndarray,
+                 read_len: np.ndarray):
+        self.ctx = ctx
+        self.cigars = cigars  # keep alive: hb_overlap.cigar points into it
+        self.ovl = Context.make_overlaps(ovl9, cigars, cig_off)
+        self.aln_off = np.ascontiguousarray(aln_off, dtype=np.uint64)
+        self.read_len = np.ascontiguousarray(read_len, dtype=np.uint32)
+
+    def windowing(self, t_begin: int, t_end: int, threads: int):
+        H = _host_lib()
+        off = np.zeros(t_end - t_begin + 1, dtype=np.uint64)
+        rc = H.hbh_windowing(self.ovl.ctypes.data, self.aln_off.ctypes.data, self.read_len.ctypes.data, self.ctx.window_size,
+                             t_begin, t_end, threads, off.ctypes.data, None, 0)
+        if rc != 0:
+            raise HerroError(rc, "windowing failed")
+        ow = np.zeros(max(int(off[-1]), 1), dtype=OVERLAP_WINDOW_DTYPE)
+        rc = H.hbh_windowing(self.ovl.ctypes.data, self.aln_off.ctypes.data, self.read_len.ctypes.data, self.ctx.window_size,
+                             t_begin, t_end, threads, off.ctypes.data, ow.ctypes.data, len(ow))
+        if rc != 0:
+            raise HerroError(rc, "windowing failed")
+        return ow, off
+
+    def run(self, t_begin: int, t_end: int, threads: int, windows=None) -> dict:
+        H = _host_lib()
+        out3 = np.zeros(3, dtype=np.uint64)
+        chk = C.c_uint64()
+        sec = C.c_double()
+        ow_p = windows[0].ctypes.data if windows is not None else None
+        off_p = windows[1].ctypes.data if windows is not None else None
+        rc = H.hbh_run(self.ctx._h, self.ovl.ctypes.data, self.aln_off.ctypes.data, self.read_len.ctypes.data,
+                       self.ctx.window_size, t_begin, t_end, threads, ow_p, off_p, out3.ctypes.data, C.byref(chk), C.byref(sec))
+        if rc != 0:
+            raise HerroError(rc, self.ctx._L.hb_last_error(self.ctx._h).decode())
+        return dict(bases=int(out3[0]), records=int(out3[1]), targets=int(out3[2]), checksum=int(chk.value), seconds=sec.value)
 
 
 # ------------------------------------------------------------------------------------------

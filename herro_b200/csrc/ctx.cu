@@ -66,12 +66,53 @@ struct PinBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// grow-only pinned host array: target batches are staged directly in page-locked memory so the
+// launch worker can cudaMemcpyAsync from them without a second copy
+template <class T>
+struct PinVec {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    PinVec() {}
+    PinVec(const PinVec&) = delete;
+    PinVec& operator=(const PinVec&) = delete;
+    PinVec(PinVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    PinVec& operator=(PinVec&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; }
+        return *this;
+    }
+    ~PinVec() { release(); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t ncap = std::max<size_t>(want + want / 2, 1024);
+        T* np = nullptr;
+        if (cudaMallocHost((void**)&np, ncap * sizeof(T)) != cudaSuccess) return false;
+        if (n) memcpy(np, p, n * sizeof(T));
+        if (p) cudaFreeHost(p);
+        p = np;
+        cap = ncap;
+        return true;
+    }
+    bool push_back(const T& v) { if (!reserve(n + 1)) return false; p[n++] = v; return true; }
+    bool append(const T* src, size_t k) { if (!reserve(n + k)) return false; if (k) memcpy(p + n, src, k * sizeof(T)); n += k; return true; }
+    bool resize(size_t k) { if (!reserve(k)) return false; n = k; return true; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    void clear() { n = 0; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+};
+
 struct HostBatch {
-    std::vector<DevTarget> tgt;
-    std::vector<DevWin> win;
-    std::vector<DevOverlap> ovl;
-    std::vector<DevOW> ow;
-    std::vector<uint8_t> cig;
+    PinVec<DevTarget> tgt;
+    PinVec<DevWin> win;
+    PinVec<DevOverlap> ovl;
+    PinVec<DevOW> ow;
+    PinVec<uint8_t> cig;
     uint64_t op_cap = 0;
     void clear() { tgt.clear(); win.clear(); ovl.clear(); ow.clear(); cig.clear(); op_cap = 0; }
 };
@@ -137,6 +178,7 @@ struct hb_ctx {
     std::thread worker;
     std::condition_variable cv_work, cv_idle;
     std::deque<HostBatch> queue;
+    std::vector<HostBatch> pool;  // recycled staging batches (keep their pinned capacity)
     bool stop = false, busy = false;
     int worker_rc = HB_OK;
     std::string worker_err;
@@ -293,7 +335,7 @@ int load_weights(hb_ctx* ctx, const char* path) {
 
 // ---------------------------------------------------------------------------------- batch run
 template <class T>
-size_t vbytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
+size_t vbytes(const PinVec<T>& v) { return v.size() * sizeof(T); }
 
 int ensure_batch_buffers(hb_ctx* ctx, const HostBatch& hbt) {
     const size_t nt = hbt.tgt.size(), nw = hbt.win.size(), no = hbt.ovl.size(), now_ = hbt.ow.size();
@@ -429,20 +471,12 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     int rc = ensure_batch_buffers(ctx, hbt);
     if (rc) return rc;
     const size_t nt = hbt.tgt.size(), nw = hbt.win.size();
-    // ---- H2D through one pinned staging area
+    // ---- H2D straight from the pinned staging arrays of the batch
     const size_t sz[5] = {vbytes(hbt.tgt), vbytes(hbt.win), vbytes(hbt.ovl), vbytes(hbt.ow), hbt.cig.size()};
-    size_t off[6] = {0};
-    for (int i = 0; i < 5; i++) off[i + 1] = (off[i] + sz[i] + 255) & ~(size_t)255;
-    CK(ctx->pin_in.ensure(off[5] + 256));
-    uint8_t* pin = ctx->pin_in.as<uint8_t>();
-    memcpy(pin + off[0], hbt.tgt.data(), sz[0]);
-    memcpy(pin + off[1], hbt.win.data(), sz[1]);
-    memcpy(pin + off[2], hbt.ovl.data(), sz[2]);
-    memcpy(pin + off[3], hbt.ow.data(), sz[3]);
-    memcpy(pin + off[4], hbt.cig.data(), sz[4]);
+    const void* src[5] = {hbt.tgt.data(), hbt.win.data(), hbt.ovl.data(), hbt.ow.data(), hbt.cig.data()};
     void* dst[5] = {ctx->d_tgt.p, ctx->d_win.p, ctx->d_ovl.p, ctx->d_ow.p, ctx->d_cig.p};
     for (int i = 0; i < 5; i++)
-        if (sz[i]) CK(cudaMemcpyAsync(dst[i], pin + off[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+        if (sz[i]) CK(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
     S.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
 
     if (ctx->rows_cap == 0) { rc = ensure_row_buffers(ctx, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
@@ -568,7 +602,7 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     // ---- publish: results, counters and the metadata for the debug taps / replay
     LastLaunch ll;
     ll.valid = true;
-    ll.win = hbt.win;
+    ll.win.assign(hbt.win.begin(), hbt.win.end());
     ll.w_L.assign(h_L, h_L + nw);
     ll.w_nsel.assign(h_nsel, h_nsel + nw);
     ll.w_nsup.assign(h_nsup, h_nsup + nw);
@@ -602,7 +636,8 @@ void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk) {
     if (ctx->hbatch.tgt.empty()) return;
     ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });  // back-pressure: at most 2 staged batches
     ctx->queue.push_back(std::move(ctx->hbatch));
-    ctx->hbatch = HostBatch();
+    if (!ctx->pool.empty()) { ctx->hbatch = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
+    else ctx->hbatch = HostBatch();
     ctx->cv_work.notify_one();
 }
 
@@ -624,6 +659,8 @@ void worker_main(hb_ctx* ctx) {
             if (ctx->worker_rc == HB_OK) ctx->worker_rc = rc;
             for (const auto& t : hbt.tgt) ctx->results.push_back(Result{t.rid, rc, {}, {}});
         }
+        hbt.clear();
+        ctx->pool.push_back(std::move(hbt));
         ctx->busy = false;
         ctx->cv_idle.notify_all();
     }
@@ -653,8 +690,7 @@ int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, u
     const uint32_t ovl_base = (uint32_t)hbt.ovl.size(), win_base = (uint32_t)hbt.win.size(), ow_base = (uint32_t)hbt.ow.size();
     for (uint32_t i = 0; i < n_ovl; i++) {
         DevOverlap d{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx};
-        hbt.cig.insert(hbt.cig.end(), ovl[i].cigar, ovl[i].cigar + ovl[i].cigar_len);
-        hbt.ovl.push_back(d);
+        if (!hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len) || !hbt.ovl.push_back(d)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
     }
     // bucket the overlap-windows by window, keeping push order (= alignment order) inside each
     std::vector<uint32_t> cnt(n_windows + 1, 0);
@@ -666,9 +702,9 @@ int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, u
         d.len = (w == n_windows - 1) ? len - w * W : W;
         d.ow_begin = ow_base + cnt[w];
         d.ow_end = ow_base + cnt[w + 1];
-        hbt.win.push_back(d);
+        if (!hbt.win.push_back(d)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
     }
-    hbt.ow.resize(ow_base + n_ow);
+    if (!hbt.ow.resize(ow_base + n_ow)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
     std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
     for (uint32_t i = 0; i < n_ow; i++) {
         const hb_overlap_window& s = ow[i];
@@ -681,7 +717,8 @@ int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, u
         d.op_base = (uint32_t)hbt.op_cap;
         hbt.op_cap += (d.cei - d.csi) / 2 + 1;
     }
-    hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl});
+    if (!hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl}))
+        return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
     if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk);
     return HB_OK;
 }
@@ -832,6 +869,7 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
                      const hb_overlap_window* ow, uint32_t n_ow) {
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
     return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ow, n_ow);
 }
 
@@ -849,6 +887,7 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
             return fail(ctx, HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
     }
     std::unique_lock<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
     return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
 }
 

@@ -1,0 +1,135 @@
+// harness.cpp — C++ host harness that stands in for the Rust binary's thread topology
+// (src/lib.rs:139-205) on top of the public C ABI only (include/herro_b200.h):
+//
+//   `threads` feature threads pull target ids from a shared counter (the MPMC alignment channel,
+//   src/lib.rs:136,159-187) and call hb_submit_target / hb_submit_alignments;
+//   one consumer thread polls hb_poll_corrected like consensus_worker -> correction_writer
+//   (src/lib.rs:198-199,267-291) and, when the producers are done, hb_flush()es.
+//
+// There is no Rust toolchain in the build image; tests and bench.py drive this through ctypes.
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/herro_b200.h"
+
+extern "C" {
+
+// Parallel host windowing (what the Rust feature threads do before submitting): fills ow_off[n_t+1]
+// and, if ow_out != NULL (cap records), the windows of targets [t_begin, t_end) back to back.
+// Call once with ow_out == NULL to size, then again to fill.  Returns 0 or an hb_status.
+int hbh_windowing(const hb_overlap* ovl_all, const uint64_t* aln_off, const uint32_t* read_len, uint32_t window,
+                  uint32_t t_begin, uint32_t t_end, int threads, uint64_t* ow_off, hb_overlap_window* ow_out, uint64_t cap) {
+    const uint32_t nt = t_end - t_begin;
+    std::vector<std::vector<hb_overlap_window>> per(nt);
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> rc{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t k = next.fetch_add(1);
+            if (k >= nt) break;
+            const uint32_t t = t_begin + k;
+            const uint32_t n_ovl = (uint32_t)(aln_off[t + 1] - aln_off[t]);
+            const uint32_t nw = (read_len[t] + window - 1) / window;
+            std::vector<hb_overlap_window>& v = per[k];
+            v.resize((size_t)n_ovl * (nw + 1) + 1);
+            uint32_t n = 0;
+            const int r = hb_extract_windows(ovl_all + aln_off[t], n_ovl, window, nw, v.data(), (uint32_t)v.size(), &n);
+            if (r != 0) { rc = r; n = 0; }
+            v.resize(n);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < (threads > 0 ? threads : 1); i++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    ow_off[0] = 0;
+    for (uint32_t k = 0; k < nt; k++) ow_off[k + 1] = ow_off[k] + per[k].size();
+    if (ow_out) {
+        if (ow_off[nt] > cap) return HB_ERR_CAPACITY;
+        for (uint32_t k = 0; k < nt; k++)
+            if (!per[k].empty()) memcpy(ow_out + ow_off[k], per[k].data(), per[k].size() * sizeof(hb_overlap_window));
+    }
+    return rc;
+}
+
+// Run targets [t_begin, t_end).  ow_all/ow_off: precomputed windows (hbh_windowing) or NULL to let the
+// library window the alignments (hb_submit_alignments).  out3 = {corrected bases, records (segments),
+// targets that produced output}; checksum = order-independent hash of (rid, segment bytes).
+int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, const uint32_t* read_len, uint32_t window,
+            uint32_t t_begin, uint32_t t_end, int threads, const hb_overlap_window* ow_all, const uint64_t* ow_off,
+            uint64_t* out3, uint64_t* checksum, double* seconds) {
+    if (!ctx || !ovl_all || !aln_off || !read_len || !out3 || !seconds) return HB_ERR_ARG;
+    std::atomic<uint32_t> next{t_begin};
+    std::atomic<int> rc{0};
+    std::atomic<int> producers_left{threads > 0 ? threads : 1};
+    const auto t0 = std::chrono::steady_clock::now();
+    auto feature_thread = [&]() {
+        for (;;) {
+            const uint32_t t = next.fetch_add(1);
+            if (t >= t_end || rc.load() != 0) break;
+            const uint32_t n_ovl = (uint32_t)(aln_off[t + 1] - aln_off[t]);
+            if (n_ovl == 0) continue;  // reads that never appear as a target (src/overlaps.rs:189-192)
+            int r;
+            if (ow_all) {
+                const uint32_t k = t - t_begin;
+                r = hb_submit_target(ctx, t, (read_len[t] + window - 1) / window, ovl_all + aln_off[t], n_ovl, ow_all + ow_off[k],
+                                     (uint32_t)(ow_off[k + 1] - ow_off[k]));
+            } else {
+                r = hb_submit_alignments(ctx, t, ovl_all + aln_off[t], n_ovl);
+            }
+            if (r != 0) rc = r;
+        }
+        producers_left.fetch_sub(1);
+    };
+    uint64_t bases = 0, records = 0, targets = 0, sum = 0;
+    auto consumer = [&]() {
+        bool flushed = false;
+        for (;;) {
+            uint32_t rid = 0, n = 0;
+            uint8_t* seqs = nullptr;
+            uint32_t* lens = nullptr;
+            const int r = hb_poll_corrected(ctx, &rid, &seqs, &lens, &n);
+            if (r == 1) {
+                uint64_t h = 1469598103934665603ull ^ rid;
+                size_t off = 0;
+                for (uint32_t k = 0; k < n; k++) {
+                    bases += lens[k];
+                    for (uint32_t i = 0; i < lens[k]; i++) h = (h ^ seqs[off + i]) * 1099511628211ull;
+                    h = (h ^ 0xff) * 1099511628211ull;
+                    off += lens[k];
+                }
+                records += n;
+                targets += n ? 1 : 0;
+                sum += h;
+                hb_release_result(ctx, seqs);
+            } else if (r == 0) {
+                if (producers_left.load() == 0) {
+                    if (flushed) break;
+                    const int f = hb_flush(ctx);
+                    if (f != 0) rc = f;
+                    flushed = true;
+                } else {
+                    std::this_thread::sleep_for(std::chrono::microseconds(100));
+                }
+            } else {
+                if (seqs) hb_release_result(ctx, seqs);
+                rc = r;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < (threads > 0 ? threads : 1); i++) th.emplace_back(feature_thread);
+    std::thread cons(consumer);
+    for (auto& t : th) t.join();
+    cons.join();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    out3[0] = bases; out3[1] = records; out3[2] = targets;
+    if (checksum) *checksum = sum;
+    return rc;
+}
+
+}  // extern "C"

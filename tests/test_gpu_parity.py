@@ -45,3 +45,21 @@ def test_launch_batching_invariance():
     b = helpers.run_product(rs, model, 4096, 64, launch_targets=3)
     assert a["segments"] == b["segments"]
     assert a["stats"]["device_launches"] == 1 and b["stats"]["device_launches"] > 1
+
+
+def test_host_harness_matches_python_path():
+    """C++ harness (feature threads + consumer over the C ABI) == single-threaded ctypes path."""
+    from herro_b200 import Context, api
+    rs = helpers.small_readset(n_reads=40, mean_len=8000, seed=9)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64)
+    want_bases = sum(len(x) for v in a["segments"].values() for x in (v or []))
+    want_targets = sum(1 for v in a["segments"].values() if v)
+    ctx = Context(model, 0, 4096, 64, launch_targets=7)
+    ctx.upload_reads(rs.seqs, rs.quals, rs.off)
+    h = api.HostHarness(ctx, rs.ovl9, rs.cigars, rs.cig_off, rs.aln_off, np.diff(rs.off).astype(np.uint32))
+    r1 = h.run(0, rs.n, 4)                                   # library does the windowing
+    r2 = h.run(0, rs.n, 3, h.windowing(0, rs.n, 2))          # host-computed windows
+    for r in (r1, r2):
+        assert r["bases"] == want_bases and r["targets"] == want_targets
+    assert r1["checksum"] == r2["checksum"]
