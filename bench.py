@@ -240,7 +240,7 @@ def main():
     st = ctx.stats()
     # ---- region 2: device stages only, inputs resident in HBM (one launch's working set is several
     #      hundred MB of matrices + activations, larger than the 126 MB L2, so no L2 flush is needed)
-    last_launch_bases = st["corrected_bases"] / max(st["device_launches"], 1)  # launches are equal-sized (same read-length distribution)
+    last_launch_bases = st["last_launch_bases"]  # what the replay re-runs
     barrier()
     ms_dev = ctx.replay_last_launch(args.steps)
     barrier()
@@ -288,7 +288,9 @@ def main():
                        "supported_positions_per_step": st["supported"] / max(st["device_launches"], 1),
                        "sharding": "one read cluster per GPU (read-id shard), no collective" if args.gpus > 1 else "single GPU",
                        "l2": "inputs larger than L2 (per-launch working set >> 126 MB)",
-                       "host_feature_threads": nthr, "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
+                       "host_feature_threads": nthr, "host_worker_busy_ms_per_step": st["ms_worker_busy"] / max(st["device_launches"], 1),
+                       "host_worker_gpu_wait_ms_per_step": st["ms_worker_gpu_wait"] / max(st["device_launches"], 1),
+                       "launches_in_e2e_region": st["device_launches"], "last_launch_targets": st["last_launch_targets"], "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
                        "model": {"channels": cfg.channels, "heads": cfg.heads, "layers": cfg.layers, "ffn": cfg.ffn,
                                  "stem_k": cfg.stem_k, "collapse": cfg.collapse, "weights": "random init (no checkpoint offline)"}},
             "e2e": {"value": bases_e2e_all / t_e2e, "unit": UNIT,

@@ -46,7 +46,9 @@ class HbStats(C.Structure):
                                           "corrected_bases", "h2d_bytes", "d2h_bytes", "kernel_launches",
                                           "device_launches", "pileup_algo_bytes", "gemm_flops", "forward_flops")] + \
                [(n, C.c_double) for n in ("ms_features", "ms_forward", "ms_consensus")] + \
-               [("ms_kernel", C.c_double * 16), ("n_kernel", C.c_uint64 * 16)]
+               [("ms_kernel", C.c_double * 16), ("n_kernel", C.c_uint64 * 16)] + \
+               [(n, C.c_uint64) for n in ("last_launch_targets", "last_launch_windows", "last_launch_bases")] + \
+               [("ms_worker_busy", C.c_double), ("ms_worker_gpu_wait", C.c_double)]
 
 
 HOST_LIB_PATH = os.path.join(_HERE, "libherro_host.so")

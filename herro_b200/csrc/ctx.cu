@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -463,8 +464,13 @@ int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launc
     return HB_OK;
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     if (hbt.tgt.empty()) return HB_OK;
+    const double t_begin = now_ms();
+    double t_wait = 0;
+#define SYNC_TIMED() do { const double t__ = now_ms(); CK(cudaStreamSynchronize(ctx->stream)); t_wait += now_ms() - t__; } while (0)
     hb_stats S{};  // merged into ctx->stats under the lock at the end
     std::vector<Result> out_results;
     const uint32_t W = ctx->opt.window_size;
@@ -499,7 +505,7 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
         launches += launch_features_c1(b, ctx->stream, ctx->kt);  // ref_lmax + scan; the work list needs its buffers first
         CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_TIMED();
         total_rows = (uint64_t)h_cnt[CNT_TOTAL_ROWS] | ((uint64_t)h_cnt[CNT_TOTAL_ROWS + 1] << 32);
         if (!h_cnt[CNT_OVERFLOW]) break;
         if (attempt >= 2) return fail(ctx, HB_ERR_CAPACITY, "row arena overflow persisted after regrowth");
@@ -531,11 +537,11 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     CK(cudaMemcpyAsync(h_nsup, b.w_nsup, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_terr, b.tgt_err, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_sel, b.sel_ow, nw * TOP_K * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_TIMED();
     const uint64_t total_out = (uint64_t)h_cnt[CNT_TOTAL_OUT] | ((uint64_t)h_cnt[CNT_TOTAL_OUT + 1] << 32);
     CK(ctx->pin_out.ensure(total_out + 16));
     if (total_out) CK(cudaMemcpyAsync(ctx->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_TIMED();
     S.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
 
     // ---- timing
@@ -617,9 +623,13 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     ll.n_sup = n_sup;
     ll.total_rows = total_rows;
     ll.view = b;
+    S.ms_worker_busy = now_ms() - t_begin;
+    S.ms_worker_gpu_wait = t_wait;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         hb_stats& T = ctx->stats;
+        T.ms_worker_busy += S.ms_worker_busy; T.ms_worker_gpu_wait += S.ms_worker_gpu_wait;
+        T.last_launch_targets = nt; T.last_launch_windows = nw; T.last_launch_bases = corrected;
         T.targets += S.targets; T.windows += S.windows; T.overlap_windows += S.overlap_windows; T.rows += S.rows;
         T.supported += S.supported; T.corrected_bases += S.corrected_bases; T.h2d_bytes += S.h2d_bytes;
         T.d2h_bytes += S.d2h_bytes; T.kernel_launches += S.kernel_launches; T.device_launches += S.device_launches;
@@ -632,9 +642,14 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     return HB_OK;
 }
 
-void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk) {
-    if (ctx->hbatch.tgt.empty()) return;
-    ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });  // back-pressure: at most 2 staged batches
+void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, bool force) {
+    for (;;) {
+        if (ctx->hbatch.tgt.empty() || (!force && ctx->hbatch.tgt.size() < ctx->opt.launch_targets)) return;
+        if (ctx->queue.size() < 2) break;
+        // back-pressure: at most 2 staged batches.  The lock is released while waiting, so another feature thread
+        // may have appended to (or already enqueued) the current batch: re-check after waking.
+        ctx->cv_idle.wait(lk);
+    }
     ctx->queue.push_back(std::move(ctx->hbatch));
     if (!ctx->pool.empty()) { ctx->hbatch = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
     else ctx->hbatch = HostBatch();
@@ -719,7 +734,7 @@ int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, u
     }
     if (!hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl}))
         return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
-    if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk);
+    if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk, false);
     return HB_OK;
 }
 
@@ -905,7 +920,7 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
 int hb_flush(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
-    enqueue_current(ctx, lk);
+    enqueue_current(ctx, lk, true);
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     const int rc = ctx->worker_rc;
     if (rc != HB_OK) { ctx->err = ctx->worker_err; ctx->worker_rc = HB_OK; }

@@ -140,6 +140,9 @@ typedef struct hb_stats {
     double ms_features, ms_forward, ms_consensus;  /* CUDA-event time per stage, summed over launches      */
     double ms_kernel[HB_NUM_KERNEL_CLASSES];       /* CUDA-event time per kernel class (timed launches)    */
     uint64_t n_kernel[HB_NUM_KERNEL_CLASSES];      /* launches per kernel class                            */
+    uint64_t last_launch_targets, last_launch_windows, last_launch_bases; /* what hb_replay_last_launch re-runs */
+    double ms_worker_busy;   /* host wall time the launch worker spent inside launches (staging+GPU+copy-back) */
+    double ms_worker_gpu_wait; /* of which: blocked in stream synchronisation                               */
 } hb_stats;
 int hb_get_stats(hb_ctx* ctx, hb_stats* out);
 int hb_reset_stats(hb_ctx* ctx);
