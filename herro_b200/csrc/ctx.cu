@@ -73,12 +73,13 @@ template <class T>
 struct PinVec {
     T* p = nullptr;
     size_t n = 0, cap = 0;
+    int dev = 0;  // device whose context owns the allocation (set before first growth)
     PinVec() {}
     PinVec(const PinVec&) = delete;
     PinVec& operator=(const PinVec&) = delete;
-    PinVec(PinVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    PinVec(PinVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap), dev(o.dev) { o.p = nullptr; o.n = o.cap = 0; }
     PinVec& operator=(PinVec&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; dev = o.dev; o.p = nullptr; o.n = o.cap = 0; }
         return *this;
     }
     ~PinVec() { release(); }
@@ -87,7 +88,9 @@ struct PinVec {
         if (want <= cap) return true;
         size_t ncap = std::max<size_t>(want + want / 2, 1024);
         T* np = nullptr;
-        if (cudaMallocHost((void**)&np, ncap * sizeof(T)) != cudaSuccess) return false;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) cudaSetDevice(dev);  // growth is rare: only then touch the runtime
+        if (cudaHostAlloc((void**)&np, ncap * sizeof(T), cudaHostAllocPortable) != cudaSuccess) return false;
         if (n) memcpy(np, p, n * sizeof(T));
         if (p) cudaFreeHost(p);
         p = np;
@@ -115,6 +118,8 @@ struct HostBatch {
     PinVec<DevOW> ow;
     PinVec<uint8_t> cig;
     uint64_t op_cap = 0;
+    HostBatch() {}
+    explicit HostBatch(int dev) { tgt.dev = win.dev = ovl.dev = ow.dev = cig.dev = dev; }
     void clear() { tgt.clear(); win.clear(); ovl.clear(); ow.clear(); cig.clear(); op_cap = 0; }
 };
 
@@ -652,7 +657,7 @@ void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, bool force) 
     }
     ctx->queue.push_back(std::move(ctx->hbatch));
     if (!ctx->pool.empty()) { ctx->hbatch = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
-    else ctx->hbatch = HostBatch();
+    else ctx->hbatch = HostBatch(ctx->device);
     ctx->cv_work.notify_one();
 }
 
@@ -681,59 +686,83 @@ void worker_main(hb_ctx* ctx) {
     }
 }
 
-int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
-                  const hb_overlap_window* ow, uint32_t n_ow) {
+// Validation and the per-window bucketing of a target run on the calling (feature) thread without the
+// context lock; only the final copy into the shared staging batch is serialised.
+struct PreparedTarget {
+    uint32_t rid, n_windows, len;
+    std::vector<uint32_t> win_begin;  // [n_windows+1] CSR of the bucketed overlap-windows
+    std::vector<DevOW> ow;            // bucketed by window, push order kept; ovl/win indices target-local
+    uint64_t cig_bytes = 0;
+};
+
+int prepare_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
+                   const hb_overlap_window* ow, uint32_t n_ow, PreparedTarget& P) {
     if (!ctx->have_reads) return fail(ctx, HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
     if (rid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "rid out of range");
     const uint32_t W = ctx->opt.window_size;
     const uint32_t len = ctx->read_len[rid];
     if (n_windows != (len + W - 1) / W) return fail(ctx, HB_ERR_ARG, "n_windows != ceil(read_len / window_size)");
     if ((n_ovl && !ovl) || (n_ow && !ow)) return fail(ctx, HB_ERR_ARG, "null array");
+    uint64_t cb = 0;
     for (uint32_t i = 0; i < n_ovl; i++) {
         if (ovl[i].tid != rid) return fail(ctx, HB_ERR_ARG, "overlap.tid != rid (alignments must be grouped by target)");
         if (ovl[i].qid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "overlap.qid out of range");
         if (!ovl[i].cigar && ovl[i].cigar_len) return fail(ctx, HB_ERR_ARG, "null cigar");
         if (ovl[i].strand > 1) return fail(ctx, HB_ERR_ARG, "strand must be 0 or 1");
+        cb += ovl[i].cigar_len;
     }
+    P.rid = rid; P.n_windows = n_windows; P.len = len; P.cig_bytes = cb;
+    P.win_begin.assign(n_windows + 1, 0);
     for (uint32_t i = 0; i < n_ow; i++) {
         if (ow[i].overlap_idx >= n_ovl || ow[i].window_idx >= n_windows) return fail(ctx, HB_ERR_ARG, "overlap_window index out of range");
         if (ow[i].cigar_end_idx < ow[i].cigar_start_idx || ow[i].cigar_end_idx > ovl[ow[i].overlap_idx].cigar_len)
             return fail(ctx, HB_ERR_ARG, "overlap_window cigar range out of bounds");
+        P.win_begin[ow[i].window_idx + 1]++;
     }
+    for (uint32_t w = 0; w < n_windows; w++) P.win_begin[w + 1] += P.win_begin[w];
+    // bucket by window, keeping push order (= alignment order) inside each
+    P.ow.resize(n_ow);
+    std::vector<uint32_t> fill(P.win_begin.begin(), P.win_begin.end() - 1);
+    for (uint32_t i = 0; i < n_ow; i++) {
+        const hb_overlap_window& s = ow[i];
+        P.ow[fill[s.window_idx]++] = DevOW{s.overlap_idx, s.window_idx, s.tstart, s.qstart, s.qend, s.cigar_start_idx,
+                                           s.cigar_start_offset, s.cigar_end_idx, s.cigar_end_offset, 0};
+    }
+    return HB_OK;
+}
+
+int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, const PreparedTarget& P, const hb_overlap* ovl, uint32_t n_ovl) {
+    const uint32_t W = ctx->opt.window_size;
     HostBatch& hbt = ctx->hbatch;
     const uint32_t t_idx = (uint32_t)hbt.tgt.size();
     const uint32_t ovl_base = (uint32_t)hbt.ovl.size(), win_base = (uint32_t)hbt.win.size(), ow_base = (uint32_t)hbt.ow.size();
-    for (uint32_t i = 0; i < n_ovl; i++) {
-        DevOverlap d{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx};
-        if (!hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len) || !hbt.ovl.push_back(d)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
-    }
-    // bucket the overlap-windows by window, keeping push order (= alignment order) inside each
-    std::vector<uint32_t> cnt(n_windows + 1, 0);
-    for (uint32_t i = 0; i < n_ow; i++) cnt[ow[i].window_idx + 1]++;
-    for (uint32_t w = 0; w < n_windows; w++) cnt[w + 1] += cnt[w];
-    for (uint32_t w = 0; w < n_windows; w++) {
-        DevWin d{};
-        d.tgt = t_idx; d.rid = rid; d.wid = w; d.tstart = w * W;
-        d.len = (w == n_windows - 1) ? len - w * W : W;
-        d.ow_begin = ow_base + cnt[w];
-        d.ow_end = ow_base + cnt[w + 1];
-        if (!hbt.win.push_back(d)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
-    }
-    if (!hbt.ow.resize(ow_base + n_ow)) return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
-    std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
-    for (uint32_t i = 0; i < n_ow; i++) {
-        const hb_overlap_window& s = ow[i];
-        DevOW d{ovl_base + s.overlap_idx, win_base + s.window_idx, s.tstart, s.qstart, s.qend, s.cigar_start_idx,
-                s.cigar_start_offset, s.cigar_end_idx, s.cigar_end_offset, 0};
-        hbt.ow[ow_base + fill[s.window_idx]++] = d;
-    }
-    for (uint32_t i = 0; i < n_ow; i++) {
-        DevOW& d = hbt.ow[ow_base + i];
-        d.op_base = (uint32_t)hbt.op_cap;
-        hbt.op_cap += (d.cei - d.csi) / 2 + 1;
-    }
-    if (!hbt.tgt.push_back(DevTarget{rid, win_base, win_base + n_windows, ovl_base, ovl_base + n_ovl}))
+    const uint32_t n_ow = (uint32_t)P.ow.size();
+    if (!hbt.ovl.reserve(ovl_base + n_ovl) || !hbt.cig.reserve(hbt.cig.size() + P.cig_bytes) || !hbt.win.reserve(win_base + P.n_windows) ||
+        !hbt.ow.resize(ow_base + n_ow) || !hbt.tgt.reserve(t_idx + 1))
         return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
+    for (uint32_t i = 0; i < n_ovl; i++) {
+        hbt.ovl.push_back(DevOverlap{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx});
+        hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len);
+    }
+    for (uint32_t w = 0; w < P.n_windows; w++) {
+        DevWin d{};
+        d.tgt = t_idx; d.rid = P.rid; d.wid = w; d.tstart = w * W;
+        d.len = (w == P.n_windows - 1) ? P.len - w * W : W;
+        d.ow_begin = ow_base + P.win_begin[w];
+        d.ow_end = ow_base + P.win_begin[w + 1];
+        hbt.win.push_back(d);
+    }
+    uint64_t opc = hbt.op_cap;
+    for (uint32_t i = 0; i < n_ow; i++) {
+        DevOW d = P.ow[i];
+        d.ovl += ovl_base;
+        d.win += win_base;
+        d.op_base = (uint32_t)opc;
+        opc += (d.cei - d.csi) / 2 + 1;
+        hbt.ow[ow_base + i] = d;
+    }
+    hbt.op_cap = opc;
+    hbt.tgt.push_back(DevTarget{P.rid, win_base, win_base + P.n_windows, ovl_base, ovl_base + n_ovl});
     if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk, false);
     return HB_OK;
 }
@@ -777,6 +806,7 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
     int rc = load_weights(ctx, model_path);
     if (rc) return bail(rc);
+    ctx->hbatch = HostBatch(ctx->device);
     ctx->worker = std::thread(worker_main, ctx);
     *out = ctx;
     return HB_OK;
@@ -883,27 +913,34 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
 int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
                      const hb_overlap_window* ow, uint32_t n_ow) {
     if (!ctx) return HB_ERR_ARG;
+    PreparedTarget P;
+    t_err_sink = nullptr;
+    std::string local_err;
+    {   // validation errors are written to a local string first: ctx->err is shared between feature threads
+        t_err_sink = &local_err;
+        const int rc = prepare_target(ctx, rid, n_windows, ovl, n_ovl, ow, n_ow, P);
+        t_err_sink = nullptr;
+        if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
+    }
     std::unique_lock<std::mutex> lk(ctx->mu);
-    cudaSetDevice(ctx->device);
-    return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ow, n_ow);
+    return append_target(ctx, lk, P, ovl, n_ovl);
 }
 
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl) {
     if (!ctx) return HB_ERR_ARG;
-    if (!ctx->have_reads) return fail(ctx, HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
-    if (rid >= ctx->n_reads) return fail(ctx, HB_ERR_ARG, "rid out of range");
-    if (n_ovl && !ovl) return fail(ctx, HB_ERR_ARG, "null array");
+    auto fail_locked = [&](int code, const std::string& msg) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = msg; return code; };
+    if (!ctx->have_reads) return fail_locked(HB_ERR_STATE, "hb_upload_reads must be called before submitting targets");
+    if (rid >= ctx->n_reads) return fail_locked(HB_ERR_ARG, "rid out of range");
+    if (n_ovl && !ovl) return fail_locked(HB_ERR_ARG, "null array");
     const uint32_t W = ctx->opt.window_size;
     const uint32_t n_windows = (ctx->read_len[rid] + W - 1) / W;
     std::vector<hb_overlap_window> ows;  // windowing runs outside the lock: feature threads do it in parallel
     for (uint32_t i = 0; i < n_ovl; i++) {
-        if (ovl[i].tid != rid) return fail(ctx, HB_ERR_ARG, "overlap.tid != rid");
+        if (ovl[i].tid != rid) return fail_locked(HB_ERR_ARG, "overlap.tid != rid");
         if (host_extract_windows(ovl[i], i, W, n_windows, ows) != 0)
-            return fail(ctx, HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
+            return fail_locked(HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
     }
-    std::unique_lock<std::mutex> lk(ctx->mu);
-    cudaSetDevice(ctx->device);
-    return append_target(ctx, lk, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
+    return hb_submit_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
 }
 
 int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
