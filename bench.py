@@ -290,7 +290,7 @@ def main():
                        "l2": "inputs larger than L2 (per-launch working set >> 126 MB)",
                        "host_feature_threads": nthr, "host_worker_busy_ms_per_step": st["ms_worker_busy"] / max(st["device_launches"], 1),
                        "host_worker_gpu_wait_ms_per_step": st["ms_worker_gpu_wait"] / max(st["device_launches"], 1),
-                       "launches_in_e2e_region": st["device_launches"], "last_launch_targets": st["last_launch_targets"], "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
+                       "launches_in_e2e_region": st["device_launches"], "harness_seconds": r_e2e["seconds"], "submit_seconds_sum": r_e2e["submit_seconds_sum"], "last_launch_targets": st["last_launch_targets"], "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
                        "model": {"channels": cfg.channels, "heads": cfg.heads, "layers": cfg.layers, "ffn": cfg.ffn,
                                  "stem_k": cfg.stem_k, "collapse": cfg.collapse, "weights": "random init (no checkpoint offline)"}},
             "e2e": {"value": bases_e2e_all / t_e2e, "unit": UNIT,

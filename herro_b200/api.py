@@ -306,7 +306,7 @@ def _host_lib():
         H = C.CDLL(HOST_LIB_PATH)
         vp, u32 = C.c_void_p, C.c_uint32
         H.hbh_windowing.argtypes = [vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, C.c_uint64]
-        H.hbh_run.argtypes = [vp, vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, vp, vp, vp]
+        H.hbh_run.argtypes = [vp, vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp]
         _host = H
     return _host
 
@@ -341,13 +341,15 @@ class HostHarness:
         out3 = np.zeros(3, dtype=np.uint64)
         chk = C.c_uint64()
         sec = C.c_double()
+        sub = C.c_double()
         ow_p = windows[0].ctypes.data if windows is not None else None
         off_p = windows[1].ctypes.data if windows is not None else None
         rc = H.hbh_run(self.ctx._h, self.ovl.ctypes.data, self.aln_off.ctypes.data, self.read_len.ctypes.data,
-                       self.ctx.window_size, t_begin, t_end, threads, ow_p, off_p, out3.ctypes.data, C.byref(chk), C.byref(sec))
+                       self.ctx.window_size, t_begin, t_end, threads, ow_p, off_p, out3.ctypes.data, C.byref(chk), C.byref(sec), C.byref(sub))
         if rc != 0:
             raise HerroError(rc, self.ctx._L.hb_last_error(self.ctx._h).decode())
-        return dict(bases=int(out3[0]), records=int(out3[1]), targets=int(out3[2]), checksum=int(chk.value), seconds=sec.value)
+        return dict(bases=int(out3[0]), records=int(out3[1]), targets=int(out3[2]), checksum=int(chk.value), seconds=sec.value,
+                    submit_seconds_sum=sub.value)
 
 
 # ------------------------------------------------------------------------------------------

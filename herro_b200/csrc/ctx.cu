@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -29,7 +31,8 @@ using namespace hb;
 namespace {
 
 thread_local std::string g_create_err;
-thread_local std::string* t_err_sink = nullptr;  // the launch worker reports into its own string
+thread_local std::string* t_err_sink = nullptr;
+std::atomic<uint64_t> g_ctx_generation{1};  // the launch worker reports into its own string
 
 struct DevBuf {
     void* p = nullptr;
@@ -162,8 +165,10 @@ struct hb_ctx {
     uint32_t ln_n = 0;
     ReadStoreView rs{};
 
-    // staging
-    HostBatch hbatch;
+    // staging: every submitting (feature) thread fills its own batch without taking the context lock;
+    // full batches are handed to the launch worker's queue
+    struct ThreadSlot { std::thread::id owner; HostBatch batch; };
+    std::vector<std::unique_ptr<ThreadSlot>> slots;
     PinBuf pin_in, pin_small, pin_out;
     DevBuf d_tgt, d_win, d_ovl, d_ow, d_cig;
     DevBuf d_op_kl, d_op_t, d_op_q, d_ow_nops, d_ow_flags, d_ow_acc, d_ow_tend, d_col_ow, d_w_n1, d_w_S;
@@ -189,6 +194,7 @@ struct hb_ctx {
     int worker_rc = HB_OK;
     std::string worker_err;
     bool idle() const { return queue.empty() && !busy; }
+    uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
 };
 
 namespace {
@@ -647,18 +653,28 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     return HB_OK;
 }
 
-void enqueue_current(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, bool force) {
-    for (;;) {
-        if (ctx->hbatch.tgt.empty() || (!force && ctx->hbatch.tgt.size() < ctx->opt.launch_targets)) return;
-        if (ctx->queue.size() < 2) break;
-        // back-pressure: at most 2 staged batches.  The lock is released while waiting, so another feature thread
-        // may have appended to (or already enqueued) the current batch: re-check after waking.
-        ctx->cv_idle.wait(lk);
-    }
-    ctx->queue.push_back(std::move(ctx->hbatch));
-    if (!ctx->pool.empty()) { ctx->hbatch = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
-    else ctx->hbatch = HostBatch(ctx->device);
+// Hand a staged batch to the launch worker (lock held).  Back-pressure: at most 2 batches wait in the queue.
+void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) {
+    if (b.tgt.empty()) return;
+    ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });
+    ctx->queue.push_back(std::move(b));
+    if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
+    else b = HostBatch(ctx->device);
     ctx->cv_work.notify_one();
+}
+
+hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
+    thread_local hb_ctx* tl_ctx = nullptr;
+    thread_local hb_ctx::ThreadSlot* tl_slot = nullptr;
+    thread_local uint64_t tl_gen = 0;
+    if (tl_ctx == ctx && tl_slot && tl_gen == ctx->generation) return tl_slot;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const auto me = std::this_thread::get_id();
+    for (auto& sl : ctx->slots)
+        if (sl->owner == me) { tl_ctx = ctx; tl_slot = sl.get(); tl_gen = ctx->generation; return tl_slot; }
+    ctx->slots.emplace_back(new hb_ctx::ThreadSlot{me, HostBatch(ctx->device)});
+    tl_ctx = ctx; tl_slot = ctx->slots.back().get(); tl_gen = ctx->generation;
+    return tl_slot;
 }
 
 void worker_main(hb_ctx* ctx) {
@@ -731,9 +747,8 @@ int prepare_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overl
     return HB_OK;
 }
 
-int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, const PreparedTarget& P, const hb_overlap* ovl, uint32_t n_ovl) {
+int append_target(hb_ctx* ctx, HostBatch& hbt, const PreparedTarget& P, const hb_overlap* ovl, uint32_t n_ovl) {
     const uint32_t W = ctx->opt.window_size;
-    HostBatch& hbt = ctx->hbatch;
     const uint32_t t_idx = (uint32_t)hbt.tgt.size();
     const uint32_t ovl_base = (uint32_t)hbt.ovl.size(), win_base = (uint32_t)hbt.win.size(), ow_base = (uint32_t)hbt.ow.size();
     const uint32_t n_ow = (uint32_t)P.ow.size();
@@ -763,7 +778,6 @@ int append_target(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, const PreparedT
     }
     hbt.op_cap = opc;
     hbt.tgt.push_back(DevTarget{P.rid, win_base, win_base + P.n_windows, ovl_base, ovl_base + n_ovl});
-    if (hbt.tgt.size() >= ctx->opt.launch_targets) enqueue_current(ctx, lk, false);
     return HB_OK;
 }
 
@@ -806,7 +820,7 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
     int rc = load_weights(ctx, model_path);
     if (rc) return bail(rc);
-    ctx->hbatch = HostBatch(ctx->device);
+    ctx->generation = g_ctx_generation.fetch_add(1);
     ctx->worker = std::thread(worker_main, ctx);
     *out = ctx;
     return HB_OK;
@@ -847,7 +861,8 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
-    if (!ctx->hbatch.tgt.empty()) return fail(ctx, HB_ERR_STATE, "hb_upload_reads with targets pending: call hb_flush first");
+    for (auto& sl : ctx->slots)
+        if (!sl->batch.tgt.empty()) return fail(ctx, HB_ERR_STATE, "hb_upload_reads with targets pending: call hb_flush first");
     if (!seq_words || !seq_len || !qual || n_reads == 0) return fail(ctx, HB_ERR_ARG, "null/empty read store");
     CK(cudaSetDevice(ctx->device));
     std::vector<uint64_t> woff(n_reads + 1, 0), qoff(n_reads + 1, 0);
@@ -922,8 +937,16 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
         t_err_sink = nullptr;
         if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
     }
-    std::unique_lock<std::mutex> lk(ctx->mu);
-    return append_target(ctx, lk, P, ovl, n_ovl);
+    hb_ctx::ThreadSlot* slot = my_slot(ctx);
+    t_err_sink = &local_err;
+    const int rc = append_target(ctx, slot->batch, P, ovl, n_ovl);
+    t_err_sink = nullptr;
+    if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
+    if (slot->batch.tgt.size() >= ctx->opt.launch_targets) {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        enqueue_batch(ctx, lk, slot->batch);
+    }
+    return HB_OK;
 }
 
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl) {
@@ -957,7 +980,7 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
 int hb_flush(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
-    enqueue_current(ctx, lk, true);
+    for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch);  // must not race with hb_submit_* (see header)
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     const int rc = ctx->worker_rc;
     if (rc != HB_OK) { ctx->err = ctx->worker_err; ctx->worker_rc = HB_OK; }

@@ -61,19 +61,22 @@ int hbh_windowing(const hb_overlap* ovl_all, const uint64_t* aln_off, const uint
 // targets that produced output}; checksum = order-independent hash of (rid, segment bytes).
 int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, const uint32_t* read_len, uint32_t window,
             uint32_t t_begin, uint32_t t_end, int threads, const hb_overlap_window* ow_all, const uint64_t* ow_off,
-            uint64_t* out3, uint64_t* checksum, double* seconds) {
+            uint64_t* out3, uint64_t* checksum, double* seconds, double* submit_seconds_sum) {
     if (!ctx || !ovl_all || !aln_off || !read_len || !out3 || !seconds) return HB_ERR_ARG;
     std::atomic<uint32_t> next{t_begin};
     std::atomic<int> rc{0};
     std::atomic<int> producers_left{threads > 0 ? threads : 1};
     const auto t0 = std::chrono::steady_clock::now();
+    std::atomic<uint64_t> submit_ns{0};
     auto feature_thread = [&]() {
+        uint64_t my_ns = 0;
         for (;;) {
             const uint32_t t = next.fetch_add(1);
             if (t >= t_end || rc.load() != 0) break;
             const uint32_t n_ovl = (uint32_t)(aln_off[t + 1] - aln_off[t]);
             if (n_ovl == 0) continue;  // reads that never appear as a target (src/overlaps.rs:189-192)
             int r;
+            const auto s0 = std::chrono::steady_clock::now();
             if (ow_all) {
                 const uint32_t k = t - t_begin;
                 r = hb_submit_target(ctx, t, (read_len[t] + window - 1) / window, ovl_all + aln_off[t], n_ovl, ow_all + ow_off[k],
@@ -81,8 +84,10 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
             } else {
                 r = hb_submit_alignments(ctx, t, ovl_all + aln_off[t], n_ovl);
             }
+            my_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - s0).count();
             if (r != 0) rc = r;
         }
+        submit_ns.fetch_add(my_ns);
         producers_left.fetch_sub(1);
     };
     uint64_t bases = 0, records = 0, targets = 0, sum = 0;
@@ -129,6 +134,7 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
     *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     out3[0] = bases; out3[1] = records; out3[2] = targets;
     if (checksum) *checksum = sum;
+    if (submit_seconds_sum) *submit_seconds_sum = (double)submit_ns.load() * 1e-9;
     return rc;
 }
 
