@@ -83,6 +83,7 @@ def load_library():
     L.hb_submit_alignments.argtypes = [vp, u32, vp, u32]
     L.hb_extract_windows.argtypes = [vp, u32, u32, u32, vp, u32, u32p]
     L.hb_flush.argtypes = [vp]
+    L.hb_set_launch_targets.argtypes = [vp, u32]
     L.hb_poll_corrected.argtypes = [vp, u32p, C.POINTER(vp), C.POINTER(vp), u32p]
     L.hb_release_result.argtypes = [vp, vp]
     L.hb_release_result.restype = None
@@ -97,7 +98,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_set_launch_targets", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -230,6 +231,9 @@ class Context:
 
     def flush(self):
         self._check(self._L.hb_flush(self._h))
+
+    def set_launch_targets(self, n: int):
+        self._check(self._L.hb_set_launch_targets(self._h, n))
 
     def poll(self):
         """-> Corrected or None; raises HerroError for a target the reference would have panicked on."""

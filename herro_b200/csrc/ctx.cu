@@ -89,7 +89,7 @@ struct PinVec {
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
     bool reserve(size_t want) {
         if (want <= cap) return true;
-        size_t ncap = std::max<size_t>(want + want / 2, 1024);
+        size_t ncap = (n == 0 && cap == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
         T* np = nullptr;
         int cur = -1;
         if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) cudaSetDevice(dev);  // growth is rare: only then touch the runtime
@@ -148,8 +148,6 @@ struct LastLaunch {  // host copies of per-window metadata of the most recent la
 struct hb_ctx {
     int device = 0;
     hb_options opt{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8]{};
     std::string err;
     std::mutex mu;
 
@@ -169,31 +167,55 @@ struct hb_ctx {
     // full batches are handed to the launch worker's queue
     struct ThreadSlot { std::thread::id owner; HostBatch batch; };
     std::vector<std::unique_ptr<ThreadSlot>> slots;
-    PinBuf pin_in, pin_small, pin_out;
-    DevBuf d_tgt, d_win, d_ovl, d_ow, d_cig;
-    DevBuf d_op_kl, d_op_t, d_op_q, d_ow_nops, d_ow_flags, d_ow_acc, d_ow_tend, d_col_ow, d_w_n1, d_w_S;
-    DevBuf d_ovl_n, d_ovl_tot, d_ovl_score, d_sel_ow, d_w_nsel, d_rowmap, d_w_L, d_w_rowbase, d_w_nsup, d_w_reflmax;
-    DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
-    DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info;
-    uint64_t rows_cap = 0;
+    PinBuf pin_in;  // staging of hb_upload_reads
+    // Two launch lanes (stream + device scratch + pinned result buffers each), one worker thread per lane:
+    // while lane A's worker does its host work (copy-back, per-read reassembly), lane B's batch keeps the GPU busy.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev[8]{};
+        KTimer kt;
+        PinBuf pin_small, pin_out;
+        DevBuf d_tgt, d_win, d_ovl, d_ow, d_cig;
+        DevBuf d_op_kl, d_op_t, d_op_q, d_ow_nops, d_ow_flags, d_ow_acc, d_ow_tend, d_col_ow, d_w_n1, d_w_S;
+        DevBuf d_ovl_n, d_ovl_tot, d_ovl_score, d_sel_ow, d_w_nsel, d_rowmap, d_w_L, d_w_rowbase, d_w_nsup, d_w_reflmax;
+        DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
+        DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info;
+        uint64_t rows_cap = 0;
+        LastLaunch last;
+        std::thread worker;
+        void release() {
+            DevBuf* bufs[] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
+                              &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
+                              &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
+                              &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
+                              &d_counters, &d_ws, &d_logits, &d_info};
+            for (DevBuf* b : bufs) b->release();
+            pin_small.release(); pin_out.release();
+            for (auto& e : ev) if (e) cudaEventDestroy(e);
+            kt.destroy();
+            if (stream) cudaStreamDestroy(stream);
+        }
+    };
+    static constexpr int NUM_LANES = 2;
+    Lane lanes[NUM_LANES];
+    int last_lane = -1;  // lane of the most recently finished launch (debug taps / replay)
     uint32_t chunk_pos = 8192;
 
     std::deque<Result> results;
     std::unordered_map<uint8_t*, void*> live;  // seqs pointer -> malloc block
     hb_stats stats{};
-    LastLaunch last;
-    KTimer kt;
 
     // launch worker: batches are processed asynchronously so that the host can stage batch i+1
     // (and drain results of batch i-1) while batch i is on the GPU
-    std::thread worker;
     std::condition_variable cv_work, cv_idle;
     std::deque<HostBatch> queue;
     std::vector<HostBatch> pool;  // recycled staging batches (keep their pinned capacity)
-    bool stop = false, busy = false;
+    bool stop = false;
+    int busy = 0;  // lanes currently inside a launch
     int worker_rc = HB_OK;
     std::string worker_err;
-    bool idle() const { return queue.empty() && !busy; }
+    bool idle() const { return queue.empty() && busy == 0; }
+    size_t cap_hint[5] = {0, 0, 0, 0, 0};  // largest batch array sizes seen (tgt, win, ovl, ow, cig)
     uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
 };
 
@@ -349,58 +371,58 @@ int load_weights(hb_ctx* ctx, const char* path) {
 template <class T>
 size_t vbytes(const PinVec<T>& v) { return v.size() * sizeof(T); }
 
-int ensure_batch_buffers(hb_ctx* ctx, const HostBatch& hbt) {
+int ensure_batch_buffers(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     const size_t nt = hbt.tgt.size(), nw = hbt.win.size(), no = hbt.ovl.size(), now_ = hbt.ow.size();
     const uint32_t W = ctx->opt.window_size;
-    CK(ctx->d_tgt.ensure(nt * sizeof(DevTarget)));
-    CK(ctx->d_win.ensure(nw * sizeof(DevWin)));
-    CK(ctx->d_ovl.ensure(std::max<size_t>(no, 1) * sizeof(DevOverlap)));
-    CK(ctx->d_ow.ensure(std::max<size_t>(now_, 1) * sizeof(DevOW)));
-    CK(ctx->d_cig.ensure(std::max<size_t>(hbt.cig.size(), 16)));
+    CK(L->d_tgt.ensure(nt * sizeof(DevTarget)));
+    CK(L->d_win.ensure(nw * sizeof(DevWin)));
+    CK(L->d_ovl.ensure(std::max<size_t>(no, 1) * sizeof(DevOverlap)));
+    CK(L->d_ow.ensure(std::max<size_t>(now_, 1) * sizeof(DevOW)));
+    CK(L->d_cig.ensure(std::max<size_t>(hbt.cig.size(), 16)));
     const size_t opc = std::max<uint64_t>(hbt.op_cap, 1);
-    CK(ctx->d_op_kl.ensure(opc * 4));
-    CK(ctx->d_op_t.ensure(opc * 4));
-    CK(ctx->d_op_q.ensure(opc * 4));
+    CK(L->d_op_kl.ensure(opc * 4));
+    CK(L->d_op_t.ensure(opc * 4));
+    CK(L->d_op_q.ensure(opc * 4));
     const size_t ow1 = std::max<size_t>(now_, 1);
-    CK(ctx->d_ow_nops.ensure(ow1 * 4));
-    CK(ctx->d_ow_flags.ensure(ow1 * 4));
-    CK(ctx->d_ow_acc.ensure(ow1 * 4));
-    CK(ctx->d_ow_tend.ensure(ow1 * 4));
-    CK(ctx->d_col_ow.ensure(ow1 * 4));
-    CK(ctx->d_w_n1.ensure(nw * 4));
-    CK(ctx->d_w_S.ensure(nw * 4));
+    CK(L->d_ow_nops.ensure(ow1 * 4));
+    CK(L->d_ow_flags.ensure(ow1 * 4));
+    CK(L->d_ow_acc.ensure(ow1 * 4));
+    CK(L->d_ow_tend.ensure(ow1 * 4));
+    CK(L->d_col_ow.ensure(ow1 * 4));
+    CK(L->d_w_n1.ensure(nw * 4));
+    CK(L->d_w_S.ensure(nw * 4));
     const size_t no1 = std::max<size_t>(no, 1);
-    CK(ctx->d_ovl_n.ensure(no1 * 4));
-    CK(ctx->d_ovl_tot.ensure(no1 * 4));
-    CK(ctx->d_ovl_score.ensure(no1 * 8));
-    CK(ctx->d_sel_ow.ensure(nw * TOP_K * 4));
-    CK(ctx->d_w_nsel.ensure(nw * 4));
-    CK(ctx->d_rowmap.ensure(nw * (size_t)(W + 1) * 4));
-    CK(ctx->d_w_L.ensure(nw * 4));
-    CK(ctx->d_w_rowbase.ensure(nw * 8));
-    CK(ctx->d_w_nsup.ensure(nw * 4));
-    CK(ctx->d_w_reflmax.ensure(nw * 4));
-    CK(ctx->d_w_supbase.ensure(nw * 8));
-    CK(ctx->d_w_outlen.ensure(nw * 4));
-    CK(ctx->d_w_outoff.ensure(nw * 8));
-    CK(ctx->d_tgt_err.ensure(nt * 4));
-    CK(ctx->d_counters.ensure(CNT_N * 4));
+    CK(L->d_ovl_n.ensure(no1 * 4));
+    CK(L->d_ovl_tot.ensure(no1 * 4));
+    CK(L->d_ovl_score.ensure(no1 * 8));
+    CK(L->d_sel_ow.ensure(nw * TOP_K * 4));
+    CK(L->d_w_nsel.ensure(nw * 4));
+    CK(L->d_rowmap.ensure(nw * (size_t)(W + 1) * 4));
+    CK(L->d_w_L.ensure(nw * 4));
+    CK(L->d_w_rowbase.ensure(nw * 8));
+    CK(L->d_w_nsup.ensure(nw * 4));
+    CK(L->d_w_reflmax.ensure(nw * 4));
+    CK(L->d_w_supbase.ensure(nw * 8));
+    CK(L->d_w_outlen.ensure(nw * 4));
+    CK(L->d_w_outoff.ensure(nw * 8));
+    CK(L->d_tgt_err.ensure(nt * 4));
+    CK(L->d_counters.ensure(CNT_N * 4));
     return HB_OK;
 }
 
-int ensure_row_buffers(hb_ctx* ctx, uint64_t rows) {
-    if (rows <= ctx->rows_cap) return HB_OK;
-    CK(ctx->d_mat_b.ensure(rows * ROW_BYTES));
-    CK(ctx->d_mat_q.ensure(rows * ROW_BYTES));
-    CK(ctx->d_row_emit.ensure(rows));
-    CK(ctx->d_sup_row.ensure(rows * 4));
-    CK(ctx->d_sup_pk.ensure(rows * 4));
-    CK(ctx->d_out.ensure(rows));
-    ctx->rows_cap = rows;
+int ensure_row_buffers(hb_ctx* ctx, hb_ctx::Lane* L, uint64_t rows) {
+    if (rows <= L->rows_cap) return HB_OK;
+    CK(L->d_mat_b.ensure(rows * ROW_BYTES));
+    CK(L->d_mat_q.ensure(rows * ROW_BYTES));
+    CK(L->d_row_emit.ensure(rows));
+    CK(L->d_sup_row.ensure(rows * 4));
+    CK(L->d_sup_pk.ensure(rows * 4));
+    CK(L->d_out.ensure(rows));
+    L->rows_cap = rows;
     return HB_OK;
 }
 
-BatchView make_view(hb_ctx* ctx, const HostBatch& hbt) {
+BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     BatchView b{};
     b.rs = ctx->rs;
     b.W = ctx->opt.window_size;
@@ -409,129 +431,129 @@ BatchView make_view(hb_ctx* ctx, const HostBatch& hbt) {
     b.n_ovl = (uint32_t)hbt.ovl.size();
     b.n_ow = (uint32_t)hbt.ow.size();
     b.batch_size = ctx->opt.batch_size;
-    b.tgt = ctx->d_tgt.as<DevTarget>();
-    b.win = ctx->d_win.as<DevWin>();
-    b.ovl = ctx->d_ovl.as<DevOverlap>();
-    b.ow = ctx->d_ow.as<DevOW>();
-    b.cig = ctx->d_cig.as<uint8_t>();
-    b.op_kl = ctx->d_op_kl.as<uint32_t>();
-    b.op_t = ctx->d_op_t.as<uint32_t>();
-    b.op_q = ctx->d_op_q.as<uint32_t>();
-    b.ow_nops = ctx->d_ow_nops.as<uint32_t>();
-    b.ow_flags = ctx->d_ow_flags.as<uint32_t>();
-    b.ow_acc = ctx->d_ow_acc.as<float>();
-    b.ow_tend = ctx->d_ow_tend.as<uint32_t>();
-    b.col_ow = ctx->d_col_ow.as<uint32_t>();
-    b.w_n1 = ctx->d_w_n1.as<uint32_t>();
-    b.w_S = ctx->d_w_S.as<uint32_t>();
-    b.ovl_n = ctx->d_ovl_n.as<uint32_t>();
-    b.ovl_tot = ctx->d_ovl_tot.as<uint32_t>();
-    b.ovl_score = ctx->d_ovl_score.as<double>();
+    b.tgt = L->d_tgt.as<DevTarget>();
+    b.win = L->d_win.as<DevWin>();
+    b.ovl = L->d_ovl.as<DevOverlap>();
+    b.ow = L->d_ow.as<DevOW>();
+    b.cig = L->d_cig.as<uint8_t>();
+    b.op_kl = L->d_op_kl.as<uint32_t>();
+    b.op_t = L->d_op_t.as<uint32_t>();
+    b.op_q = L->d_op_q.as<uint32_t>();
+    b.ow_nops = L->d_ow_nops.as<uint32_t>();
+    b.ow_flags = L->d_ow_flags.as<uint32_t>();
+    b.ow_acc = L->d_ow_acc.as<float>();
+    b.ow_tend = L->d_ow_tend.as<uint32_t>();
+    b.col_ow = L->d_col_ow.as<uint32_t>();
+    b.w_n1 = L->d_w_n1.as<uint32_t>();
+    b.w_S = L->d_w_S.as<uint32_t>();
+    b.ovl_n = L->d_ovl_n.as<uint32_t>();
+    b.ovl_tot = L->d_ovl_tot.as<uint32_t>();
+    b.ovl_score = L->d_ovl_score.as<double>();
     b.ln_table = ctx->d_ln.as<double>();
     b.ln_table_n = ctx->ln_n;
-    b.sel_ow = ctx->d_sel_ow.as<uint32_t>();
-    b.w_nsel = ctx->d_w_nsel.as<uint32_t>();
-    b.rowmap = ctx->d_rowmap.as<uint32_t>();
-    b.w_L = ctx->d_w_L.as<uint32_t>();
-    b.w_rowbase = ctx->d_w_rowbase.as<uint64_t>();
-    b.w_nsup = ctx->d_w_nsup.as<uint32_t>();
-    b.w_reflmax = ctx->d_w_reflmax.as<uint32_t>();
-    b.rows_cap = ctx->rows_cap;
-    b.mat_bases = ctx->d_mat_b.as<uint8_t>();
-    b.mat_quals = ctx->d_mat_q.as<uint8_t>();
-    b.row_emit = ctx->d_row_emit.as<uint8_t>();
-    b.sup_row = ctx->d_sup_row.as<uint32_t>();
-    b.sup_pk = ctx->d_sup_pk.as<uint32_t>();
-    b.w_supbase = ctx->d_w_supbase.as<uint64_t>();
-    b.fwd_win = ctx->d_fwd_win.as<uint32_t>();
-    b.fwd_row = ctx->d_fwd_row.as<uint32_t>();
-    b.w_outlen = ctx->d_w_outlen.as<uint32_t>();
-    b.w_outoff = ctx->d_w_outoff.as<uint64_t>();
-    b.out_bytes = ctx->d_out.as<uint8_t>();
-    b.tgt_err = ctx->d_tgt_err.as<uint32_t>();
-    b.counters = ctx->d_counters.as<uint32_t>();
+    b.sel_ow = L->d_sel_ow.as<uint32_t>();
+    b.w_nsel = L->d_w_nsel.as<uint32_t>();
+    b.rowmap = L->d_rowmap.as<uint32_t>();
+    b.w_L = L->d_w_L.as<uint32_t>();
+    b.w_rowbase = L->d_w_rowbase.as<uint64_t>();
+    b.w_nsup = L->d_w_nsup.as<uint32_t>();
+    b.w_reflmax = L->d_w_reflmax.as<uint32_t>();
+    b.rows_cap = L->rows_cap;
+    b.mat_bases = L->d_mat_b.as<uint8_t>();
+    b.mat_quals = L->d_mat_q.as<uint8_t>();
+    b.row_emit = L->d_row_emit.as<uint8_t>();
+    b.sup_row = L->d_sup_row.as<uint32_t>();
+    b.sup_pk = L->d_sup_pk.as<uint32_t>();
+    b.w_supbase = L->d_w_supbase.as<uint64_t>();
+    b.fwd_win = L->d_fwd_win.as<uint32_t>();
+    b.fwd_row = L->d_fwd_row.as<uint32_t>();
+    b.w_outlen = L->d_w_outlen.as<uint32_t>();
+    b.w_outoff = L->d_w_outoff.as<uint64_t>();
+    b.out_bytes = L->d_out.as<uint8_t>();
+    b.tgt_err = L->d_tgt_err.as<uint32_t>();
+    b.counters = L->d_counters.as<uint32_t>();
     return b;
 }
 
-int zero_scratch(hb_ctx* ctx, const BatchView& b) {
-    CK(cudaMemsetAsync(b.ovl_n, 0, std::max<size_t>(b.n_ovl, 1) * 4, ctx->stream));
-    CK(cudaMemsetAsync(b.ovl_tot, 0, std::max<size_t>(b.n_ovl, 1) * 4, ctx->stream));
-    CK(cudaMemsetAsync(b.tgt_err, 0, (size_t)b.n_tgt * 4, ctx->stream));
-    CK(cudaMemsetAsync(b.counters, 0, CNT_N * 4, ctx->stream));
+int zero_scratch(hb_ctx* ctx, hb_ctx::Lane* L, const BatchView& b) {
+    CK(cudaMemsetAsync(b.ovl_n, 0, std::max<size_t>(b.n_ovl, 1) * 4, L->stream));
+    CK(cudaMemsetAsync(b.ovl_tot, 0, std::max<size_t>(b.n_ovl, 1) * 4, L->stream));
+    CK(cudaMemsetAsync(b.tgt_err, 0, (size_t)b.n_tgt * 4, L->stream));
+    CK(cudaMemsetAsync(b.counters, 0, CNT_N * 4, L->stream));
     return HB_OK;
 }
 
 // The forward + consensus part once the number of supported positions is known.
-int launch_tail(hb_ctx* ctx, const BatchView& b, uint64_t n_sup, uint64_t* launches) {
-    *launches += launch_features_c2(b, ctx->stream, ctx->kt);
+int launch_tail(hb_ctx* ctx, hb_ctx::Lane* L, const BatchView& b, uint64_t n_sup, uint64_t* launches) {
+    *launches += launch_features_c2(b, L->stream, L->kt);
     for (uint64_t n0 = 0; n0 < n_sup; n0 += ctx->chunk_pos) {
         const uint32_t np = (uint32_t)std::min<uint64_t>(ctx->chunk_pos, n_sup - n0);
-        *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, ctx->d_ws.as<uint8_t>(), ctx->d_logits.as<float>(),
-                                          ctx->d_info.as<float>(), ctx->stream, ctx->kt);
+        *launches += launch_forward_chunk(b, ctx->wt, (uint32_t)n0, np, L->d_ws.as<uint8_t>(), L->d_logits.as<float>(),
+                                          L->d_info.as<float>(), L->stream, L->kt);
     }
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    *launches += launch_consensus(b, ctx->stream, ctx->kt);
-    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CK(cudaEventRecord(L->ev[4], L->stream));
+    *launches += launch_consensus(b, L->stream, L->kt);
+    CK(cudaEventRecord(L->ev[5], L->stream));
     return HB_OK;
 }
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-int run_batch(hb_ctx* ctx, HostBatch& hbt) {
+int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     if (hbt.tgt.empty()) return HB_OK;
     const double t_begin = now_ms();
     double t_wait = 0;
-#define SYNC_TIMED() do { const double t__ = now_ms(); CK(cudaStreamSynchronize(ctx->stream)); t_wait += now_ms() - t__; } while (0)
+#define SYNC_TIMED() do { const double t__ = now_ms(); CK(cudaStreamSynchronize(L->stream)); t_wait += now_ms() - t__; } while (0)
     hb_stats S{};  // merged into ctx->stats under the lock at the end
     std::vector<Result> out_results;
     const uint32_t W = ctx->opt.window_size;
-    int rc = ensure_batch_buffers(ctx, hbt);
+    int rc = ensure_batch_buffers(ctx, L, hbt);
     if (rc) return rc;
     const size_t nt = hbt.tgt.size(), nw = hbt.win.size();
     // ---- H2D straight from the pinned staging arrays of the batch
     const size_t sz[5] = {vbytes(hbt.tgt), vbytes(hbt.win), vbytes(hbt.ovl), vbytes(hbt.ow), hbt.cig.size()};
     const void* src[5] = {hbt.tgt.data(), hbt.win.data(), hbt.ovl.data(), hbt.ow.data(), hbt.cig.data()};
-    void* dst[5] = {ctx->d_tgt.p, ctx->d_win.p, ctx->d_ovl.p, ctx->d_ow.p, ctx->d_cig.p};
+    void* dst[5] = {L->d_tgt.p, L->d_win.p, L->d_ovl.p, L->d_ow.p, L->d_cig.p};
     for (int i = 0; i < 5; i++)
-        if (sz[i]) CK(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+        if (sz[i]) CK(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyHostToDevice, L->stream));
     S.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
 
-    if (ctx->rows_cap == 0) { rc = ensure_row_buffers(ctx, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
-    CK(ctx->pin_small.ensure(CNT_N * 4 + nw * 4 * 4 + nt * 4 + nw * TOP_K * 4 + 1024));
-    uint32_t* h_cnt = ctx->pin_small.as<uint32_t>();
+    if (L->rows_cap == 0) { rc = ensure_row_buffers(ctx, L, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
+    CK(L->pin_small.ensure(CNT_N * 4 + nw * 4 * 4 + nt * 4 + nw * TOP_K * 4 + 1024));
+    uint32_t* h_cnt = L->pin_small.as<uint32_t>();
     uint64_t launches = 0;
     BatchView b;
     uint64_t total_rows = 0;
-    ctx->kt.on = true;
-    ctx->kt.st = ctx->stream;
+    L->kt.on = true;
+    L->kt.st = L->stream;
     for (int attempt = 0;; attempt++) {
-        if (attempt) ctx->kt.discard();
-        b = make_view(ctx, hbt);
-        rc = zero_scratch(ctx, b);
+        if (attempt) L->kt.discard();
+        b = make_view(ctx, L, hbt);
+        rc = zero_scratch(ctx, L, b);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        launches += launch_features_a(b, ctx->stream, ctx->kt);
-        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        launches += launch_pileup(b, ctx->stream, ctx->kt);
-        CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-        launches += launch_features_c1(b, ctx->stream, ctx->kt);  // ref_lmax + scan; the work list needs its buffers first
-        CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(L->ev[0], L->stream));
+        launches += launch_features_a(b, L->stream, L->kt);
+        CK(cudaEventRecord(L->ev[1], L->stream));
+        launches += launch_pileup(b, L->stream, L->kt);
+        CK(cudaEventRecord(L->ev[2], L->stream));
+        launches += launch_features_c1(b, L->stream, L->kt);  // ref_lmax + scan; the work list needs its buffers first
+        CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, L->stream));
         SYNC_TIMED();
         total_rows = (uint64_t)h_cnt[CNT_TOTAL_ROWS] | ((uint64_t)h_cnt[CNT_TOTAL_ROWS + 1] << 32);
         if (!h_cnt[CNT_OVERFLOW]) break;
         if (attempt >= 2) return fail(ctx, HB_ERR_CAPACITY, "row arena overflow persisted after regrowth");
-        rc = ensure_row_buffers(ctx, total_rows + total_rows / 8 + 4096);
+        rc = ensure_row_buffers(ctx, L, total_rows + total_rows / 8 + 4096);
         if (rc) return rc;
     }
     const uint64_t n_sup = (uint64_t)h_cnt[CNT_NSUP] | ((uint64_t)h_cnt[CNT_NSUP + 1] << 32);
-    CK(ctx->d_fwd_win.ensure(std::max<uint64_t>(n_sup, 1) * 4));
-    CK(ctx->d_fwd_row.ensure(std::max<uint64_t>(n_sup, 1) * 4));
-    CK(ctx->d_logits.ensure(std::max<uint64_t>(n_sup, 1) * 5 * 4));
-    CK(ctx->d_info.ensure(std::max<uint64_t>(n_sup, 1) * 4));
-    CK(ctx->d_ws.ensure(fwd_workspace_bytes(ctx->wt, ctx->chunk_pos)));
-    b = make_view(ctx, hbt);
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    rc = launch_tail(ctx, b, n_sup, &launches);
+    CK(L->d_fwd_win.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(L->d_fwd_row.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(L->d_logits.ensure(std::max<uint64_t>(n_sup, 1) * 5 * 4));
+    CK(L->d_info.ensure(std::max<uint64_t>(n_sup, 1) * 4));
+    CK(L->d_ws.ensure(fwd_workspace_bytes(ctx->wt, ctx->chunk_pos)));
+    b = make_view(ctx, L, hbt);
+    CK(cudaEventRecord(L->ev[3], L->stream));
+    rc = launch_tail(ctx, L, b, n_sup, &launches);
     if (rc) return rc;
 
     // ---- D2H: per-window metadata, then exactly the emitted bytes
@@ -541,27 +563,27 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     uint32_t* h_nsup = h_L + nw;
     uint32_t* h_terr = h_nsup + nw;
     uint32_t* h_sel = h_terr + nt;
-    CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_outlen, b.w_outlen, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_nsel, b.w_nsel, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_L, b.w_L, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_nsup, b.w_nsup, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_terr, b.tgt_err, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_sel, b.sel_ow, nw * TOP_K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_outlen, b.w_outlen, nw * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_nsel, b.w_nsel, nw * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_L, b.w_L, nw * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_nsup, b.w_nsup, nw * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_terr, b.tgt_err, nt * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(h_sel, b.sel_ow, nw * TOP_K * 4, cudaMemcpyDeviceToHost, L->stream));
     SYNC_TIMED();
     const uint64_t total_out = (uint64_t)h_cnt[CNT_TOTAL_OUT] | ((uint64_t)h_cnt[CNT_TOTAL_OUT + 1] << 32);
-    CK(ctx->pin_out.ensure(total_out + 16));
-    if (total_out) CK(cudaMemcpyAsync(ctx->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(L->pin_out.ensure(total_out + 16));
+    if (total_out) CK(cudaMemcpyAsync(L->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, L->stream));
     SYNC_TIMED();
     S.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
 
     // ---- timing
     float ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); S.ms_features += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); S.ms_forward += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); S.ms_consensus += ms;
-    ctx->kt.collect(S.ms_kernel, S.n_kernel);
-    ctx->kt.on = false;
+    cudaEventElapsedTime(&ms, L->ev[0], L->ev[2]); S.ms_features += ms;
+    cudaEventElapsedTime(&ms, L->ev[3], L->ev[4]); S.ms_forward += ms;
+    cudaEventElapsedTime(&ms, L->ev[4], L->ev[5]); S.ms_consensus += ms;
+    L->kt.collect(S.ms_kernel, S.n_kernel);
+    L->kt.on = false;
     {
         uint64_t gf = 0;
         const uint64_t ff = forward_flops_per_pos(ctx->wt, &gf);
@@ -570,7 +592,7 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
     }
 
     // ---- per-read reassembly (src/consensus.rs:90-111,222-226)
-    const uint8_t* outb = ctx->pin_out.as<uint8_t>();
+    const uint8_t* outb = L->pin_out.as<uint8_t>();
     uint64_t o = 0, corrected = 0, algo = 0;
     for (size_t t = 0; t < nt; t++) {
         const DevTarget& tg = hbt.tgt[t];
@@ -648,19 +670,35 @@ int run_batch(hb_ctx* ctx, HostBatch& hbt) {
         T.ms_features += S.ms_features; T.ms_forward += S.ms_forward; T.ms_consensus += S.ms_consensus;
         for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) { T.ms_kernel[i] += S.ms_kernel[i]; T.n_kernel[i] += S.n_kernel[i]; }
         for (auto& r : out_results) ctx->results.push_back(std::move(r));
-        ctx->last = std::move(ll);
+        L->last = std::move(ll);
+        ctx->last_lane = (int)(L - ctx->lanes);
     }
     return HB_OK;
 }
 
-// Hand a staged batch to the launch worker (lock held).  Back-pressure: at most 2 batches wait in the queue.
+// Hand a staged batch to the launch worker (lock held); `b` is left empty (no capacity).
+// Back-pressure: at most 2 batches wait in the queue.
 void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) {
     if (b.tgt.empty()) return;
+    size_t* h = ctx->cap_hint;
+    h[0] = std::max(h[0], b.tgt.size()); h[1] = std::max(h[1], b.win.size()); h[2] = std::max(h[2], b.ovl.size());
+    h[3] = std::max(h[3], b.ow.size()); h[4] = std::max(h[4], b.cig.size());
     ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });
     ctx->queue.push_back(std::move(b));
-    if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
-    else b = HostBatch(ctx->device);
+    b = HostBatch(ctx->device);
     ctx->cv_work.notify_one();
+}
+
+// A staging batch with capacity: recycled from the pool, else allocated once at the largest size seen so far
+// (pinned allocations are slow and serialise with the worker's CUDA calls, so growth in small steps is avoided).
+void acquire_batch(hb_ctx* ctx, HostBatch& b) {
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); return; }
+    size_t h[5];
+    for (int i = 0; i < 5; i++) h[i] = ctx->cap_hint[i] + ctx->cap_hint[i] / 8;
+    lk.unlock();
+    b = HostBatch(ctx->device);
+    if (h[0]) { b.tgt.reserve(h[0]); b.win.reserve(h[1]); b.ovl.reserve(h[2]); b.ow.reserve(h[3]); b.cig.reserve(h[4]); }
 }
 
 hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
@@ -677,27 +715,29 @@ hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
     return tl_slot;
 }
 
-void worker_main(hb_ctx* ctx) {
+void worker_main(hb_ctx* ctx, int lane) {
     cudaSetDevice(ctx->device);
-    t_err_sink = &ctx->worker_err;
+    hb_ctx::Lane* L = &ctx->lanes[lane];
+    std::string my_err;
+    t_err_sink = &my_err;
     std::unique_lock<std::mutex> lk(ctx->mu);
     for (;;) {
         ctx->cv_work.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
         if (ctx->queue.empty()) break;  // stop requested and nothing left
         HostBatch hbt = std::move(ctx->queue.front());
         ctx->queue.pop_front();
-        ctx->busy = true;
+        ctx->busy++;
         ctx->cv_idle.notify_all();
         lk.unlock();
-        const int rc = run_batch(ctx, hbt);
+        const int rc = run_batch(ctx, L, hbt);
         lk.lock();
         if (rc != HB_OK) {
-            if (ctx->worker_rc == HB_OK) ctx->worker_rc = rc;
+            if (ctx->worker_rc == HB_OK) { ctx->worker_rc = rc; ctx->worker_err = my_err; }
             for (const auto& t : hbt.tgt) ctx->results.push_back(Result{t.rid, rc, {}, {}});
         }
         hbt.clear();
         ctx->pool.push_back(std::move(hbt));
-        ctx->busy = false;
+        ctx->busy--;
         ctx->cv_idle.notify_all();
     }
 }
@@ -814,44 +854,38 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     }
     if (cuda_device < 0 || cuda_device >= ndev) { ctx->err = "cuda_device out of range"; return bail(HB_ERR_ARG); }
     if (cudaSetDevice(cuda_device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(HB_ERR_CUDA); }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(HB_ERR_CUDA); }
-    for (auto& e : ctx->ev)
-        if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(HB_ERR_CUDA); }
+    for (auto& L : ctx->lanes) {
+        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(HB_ERR_CUDA); }
+        for (auto& e : L.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(HB_ERR_CUDA); }
+    }
     if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
     int rc = load_weights(ctx, model_path);
     if (rc) return bail(rc);
     ctx->generation = g_ctx_generation.fetch_add(1);
-    ctx->worker = std::thread(worker_main, ctx);
+    for (int i = 0; i < hb_ctx::NUM_LANES; i++) ctx->lanes[i].worker = std::thread(worker_main, ctx, i);
     *out = ctx;
     return HB_OK;
 }
 
 void hb_destroy(hb_ctx* ctx) {
     if (!ctx) return;
-    if (ctx->worker.joinable()) {
-        {
-            std::lock_guard<std::mutex> lk(ctx->mu);
-            ctx->stop = true;
-        }
-        ctx->cv_work.notify_all();
-        ctx->worker.join();
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stop = true;
     }
+    ctx->cv_work.notify_all();
+    for (auto& L : ctx->lanes) if (L.worker.joinable()) L.worker.join();
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& L : ctx->lanes) if (L.stream) cudaStreamSynchronize(L.stream);
     for (void* p : ctx->weight_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->d_words, &ctx->d_word_off, &ctx->d_len, &ctx->d_qual, &ctx->d_qual_off, &ctx->d_ln, &ctx->d_tgt,
-                      &ctx->d_win, &ctx->d_ovl, &ctx->d_ow, &ctx->d_cig, &ctx->d_op_kl, &ctx->d_op_t, &ctx->d_op_q,
-                      &ctx->d_ow_nops, &ctx->d_ow_flags, &ctx->d_ow_acc, &ctx->d_ow_tend, &ctx->d_col_ow, &ctx->d_w_n1,
-                      &ctx->d_w_S, &ctx->d_ovl_n, &ctx->d_ovl_tot, &ctx->d_ovl_score, &ctx->d_sel_ow, &ctx->d_w_nsel,
-                      &ctx->d_rowmap, &ctx->d_w_L, &ctx->d_w_rowbase, &ctx->d_w_nsup, &ctx->d_w_reflmax, &ctx->d_mat_b,
-                      &ctx->d_mat_q, &ctx->d_row_emit, &ctx->d_sup_row, &ctx->d_sup_pk, &ctx->d_w_supbase, &ctx->d_fwd_win,
-                      &ctx->d_fwd_row, &ctx->d_w_outlen, &ctx->d_w_outoff, &ctx->d_out, &ctx->d_tgt_err, &ctx->d_counters,
-                      &ctx->d_ws, &ctx->d_logits, &ctx->d_info};
+    DevBuf* bufs[] = {&ctx->d_words, &ctx->d_word_off, &ctx->d_len, &ctx->d_qual, &ctx->d_qual_off, &ctx->d_ln};
     for (DevBuf* b : bufs) b->release();
-    ctx->pin_in.release(); ctx->pin_small.release(); ctx->pin_out.release();
-    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
-    ctx->kt.destroy();
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto& L : ctx->lanes) L.release();
+    ctx->pin_in.release();
+    ctx->slots.clear();
+    ctx->queue.clear();
+    ctx->pool.clear();
     for (auto& kv : ctx->live) free(kv.second);
     delete ctx;
 }
@@ -938,6 +972,7 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
         if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
     }
     hb_ctx::ThreadSlot* slot = my_slot(ctx);
+    if (slot->batch.tgt.cap == 0) acquire_batch(ctx, slot->batch);
     t_err_sink = &local_err;
     const int rc = append_target(ctx, slot->batch, P, ovl, n_ovl);
     t_err_sink = nullptr;
@@ -977,10 +1012,19 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
     return HB_OK;
 }
 
+int hb_set_launch_targets(hb_ctx* ctx, uint32_t launch_targets) {
+    if (!ctx || launch_targets == 0) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->opt.launch_targets = launch_targets;
+    return HB_OK;
+}
+
 int hb_flush(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
     for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch);  // must not race with hb_submit_* (see header)
+    ctx->slots.clear();                                  // slots of finished feature threads are dropped;
+    ctx->generation = g_ctx_generation.fetch_add(1);    // live threads re-register on their next submit
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     const int rc = ctx->worker_rc;
     if (rc != HB_OK) { ctx->err = ctx->worker_err; ctx->worker_rc = HB_OK; }
@@ -1033,9 +1077,10 @@ int hb_reset_stats(hb_ctx* ctx) {
 
 static int find_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* w) {
     if (!(ctx->opt.flags & HB_FLAG_KEEP_DEBUG)) return fail(ctx, HB_ERR_STATE, "context was not created with HB_FLAG_KEEP_DEBUG");
-    if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch yet");
-    auto it = ctx->last.index.find(((uint64_t)rid << 32) | wid);
-    if (it == ctx->last.index.end()) return fail(ctx, HB_ERR_ARG, "window not part of the most recent launch");
+    if (ctx->last_lane < 0 || !ctx->lanes[ctx->last_lane].last.valid) return fail(ctx, HB_ERR_STATE, "no launch yet");
+    const LastLaunch& last = ctx->lanes[ctx->last_lane].last;
+    auto it = last.index.find(((uint64_t)rid << 32) | wid);
+    if (it == last.index.end()) return fail(ctx, HB_ERR_ARG, "window not part of the most recent launch");
     *w = it->second;
     return HB_OK;
 }
@@ -1047,9 +1092,10 @@ int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* sha
     uint32_t w;
     int rc = find_window(ctx, rid, wid, &w);
     if (rc) return rc;
-    shape4[0] = ctx->last.w_L[w];
-    shape4[1] = ctx->last.w_nsel[w];
-    shape4[2] = ctx->last.w_nsup[w];
+    const LastLaunch& last = ctx->lanes[ctx->last_lane].last;
+    shape4[0] = last.w_L[w];
+    shape4[1] = last.w_nsel[w];
+    shape4[2] = last.w_nsup[w];
     shape4[3] = 1;
     return HB_OK;
 }
@@ -1063,7 +1109,8 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
     uint32_t w;
     int rc = find_window(ctx, rid, wid, &w);
     if (rc) return rc;
-    const LastLaunch& ll = ctx->last;
+    hb_ctx::Lane* lane = &ctx->lanes[ctx->last_lane];
+    const LastLaunch& ll = lane->last;
     const uint32_t L = ll.w_L[w], ns = ll.w_nsup[w];
     const uint64_t rb = ll.w_rowbase[w], sb = ll.w_supbase[w];
     std::vector<uint8_t> tmp((size_t)L * ROW_BYTES);
@@ -1080,8 +1127,8 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
             for (uint32_t k = 0; k < ns; k++) { supported[2 * k] = (t[k] >> 8) & 0xffffu; supported[2 * k + 1] = t[k] & 0xffu; }
         }
         if (sup_rows) CK(cudaMemcpy(sup_rows, ll.view.sup_row + rb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
-        if (info_logits) CK(cudaMemcpy(info_logits, ctx->d_info.as<float>() + sb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
-        if (bases_logits) CK(cudaMemcpy(bases_logits, ctx->d_logits.as<float>() + sb * 5, (size_t)ns * 20, cudaMemcpyDeviceToHost));
+        if (info_logits) CK(cudaMemcpy(info_logits, lane->d_info.as<float>() + sb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+        if (bases_logits) CK(cudaMemcpy(bases_logits, lane->d_logits.as<float>() + sb * 5, (size_t)ns * 20, cudaMemcpyDeviceToHost));
     }
     return HB_OK;
 }
@@ -1182,26 +1229,27 @@ int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {
     std::unique_lock<std::mutex> lk(ctx->mu);
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     CK(cudaSetDevice(ctx->device));
-    if (!ctx->last.valid) return fail(ctx, HB_ERR_STATE, "no launch to replay");
-    const BatchView b = ctx->last.view;
+    if (ctx->last_lane < 0 || !ctx->lanes[ctx->last_lane].last.valid) return fail(ctx, HB_ERR_STATE, "no launch to replay");
+    hb_ctx::Lane* L = &ctx->lanes[ctx->last_lane];
+    const BatchView b = L->last.view;
     uint64_t launches = 0;
-    ctx->kt.on = false;
-    ctx->kt.st = ctx->stream;
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    L->kt.on = false;
+    L->kt.st = L->stream;
+    CK(cudaStreamSynchronize(L->stream));
+    CK(cudaEventRecord(L->ev[6], L->stream));
     for (uint32_t it = 0; it < iters; it++) {
-        int rc = zero_scratch(ctx, b);
+        int rc = zero_scratch(ctx, L, b);
         if (rc) return rc;
-        launches += launch_features_a(b, ctx->stream, ctx->kt);
-        launches += launch_pileup(b, ctx->stream, ctx->kt);
-        launches += launch_features_c1(b, ctx->stream, ctx->kt);
-        rc = launch_tail(ctx, b, ctx->last.n_sup, &launches);
+        launches += launch_features_a(b, L->stream, L->kt);
+        launches += launch_pileup(b, L->stream, L->kt);
+        launches += launch_features_c1(b, L->stream, L->kt);
+        rc = launch_tail(ctx, L, b, L->last.n_sup, &launches);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
-    ctx->kt.discard();
+    CK(cudaEventRecord(L->ev[7], L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    CK(cudaEventElapsedTime(ms, L->ev[6], L->ev[7]));
+    L->kt.discard();
     ctx->stats.kernel_launches += launches;
     return HB_OK;
 }

@@ -112,7 +112,13 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
 int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
                        hb_overlap_window* out, uint32_t cap, uint32_t* n_out);
 
-/* Launch whatever is pending and wait until every submitted target has a result queued. */
+/* Change hb_options.launch_targets (targets per device launch, staged per feature thread) for subsequent
+ * submissions.  Call between hb_flush and the next hb_submit_*. */
+int hb_set_launch_targets(hb_ctx* ctx, uint32_t launch_targets);
+
+/* Launch whatever is pending (every feature thread stages its own batch) and wait until every submitted
+ * target has a result queued.  Call it once the submitting threads are quiescent (the reference's
+ * equivalent is the alignment channel closing, src/lib.rs:186); it must not race with hb_submit_*. */
 int hb_flush(hb_ctx* ctx);
 
 /* Pop one finished target: the `(rid, Vec<Vec<u8>>)` of src/consensus.rs:253-257.
