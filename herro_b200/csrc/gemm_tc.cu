@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    // per-item bias chunk and the LayerNorm affine: read from shared memory in the epilogue (the L1 of this
+    // kernel is almost entirely carved out for the operand ring, so repeated global reads would pay L2 latency)
+    __shared__ __align__(16) float s_bias[2][BN], s_lng[BN], s_lnb[BN];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 8) {
@@ -194,10 +197,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
         }
     } else {
         // =============================== epilogue ===============================
+        if (g.mode == GEMM_OUT_F32_RES_LN) { s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t m0 = (item / g.n_chunks) * BM, n0 = (item % g.n_chunks) * BN;
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+            s_bias[acc][tid] = g.bias[n0 + tid];     // the previous user of this slot finished 2 items ago
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // epilogue warps only
+            const float* sb = s_bias[acc];
             mbar_wait(&tfull_bar[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const size_t row = (size_t)m0 + warp * 32 + lane;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                     tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = *(const float4*)(g.bias + c0 + j);
+                        const float4 bv = *(const float4*)(sb + c0 + j);
                         const float4 r = *(const float4*)(xrow + c0 + j);
                         x[c0 + j] = __uint_as_float(v[j]) + bv.x + r.x; x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bv.y + r.y;
                         x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bv.z + r.z; x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bv.w + r.w;
@@ -237,8 +244,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
-                        const float a = (x[j + e] - mean) * rstd * g.ln_g[j + e] + g.ln_b[j + e];
-                        const float b = (x[j + e + 1] - mean) * rstd * g.ln_g[j + e + 1] + g.ln_b[j + e + 1];
+                        const float a = (x[j + e] - mean) * rstd * s_lng[j + e] + s_lnb[j + e];
+                        const float b = (x[j + e + 1] - mean) * rstd * s_lng[j + e + 1] + s_lnb[j + e + 1];
                         const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
                         hi[e >> 1] = pack2(ah, bh);
                         lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                 float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *(const float4*)(g.bias + col + j);
+                    const float4 bv = *(const float4*)(sb + c0 + j);
                     o[j] = __uint_as_float(v[j]) + bv.x; o[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
                     o[j + 2] = __uint_as_float(v[j + 2]) + bv.z; o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
                 }
