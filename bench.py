@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--feature-threads", type=int, default=8, help="reference -t: host threads submitting targets")
+    ap.add_argument("--feature-threads", type=int, default=4, help="reference -t: host threads submitting targets")
     return ap.parse_args()
 
 

@@ -367,8 +367,8 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
     // With C == 128 a contraction that writes the residual stream owns whole rows in its epilogue, so the
     // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
-    static const bool fuse_env = getenv("HERRO_B200_FUSE_LN") != nullptr;  // experimental: slower than the separate kernel so far
-    const bool fuse_ln = (C == 128) && fuse_env;
+    static const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid
+    const bool fuse_ln = (C == 128) && !no_fuse;
     kt.begin(K_LAYERNORM);
     k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
     kt.end(); nl++;

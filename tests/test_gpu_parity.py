@@ -63,3 +63,26 @@ def test_host_harness_matches_python_path():
     for r in (r1, r2):
         assert r["bases"] == want_bases and r["targets"] == want_targets
     assert r1["checksum"] == r2["checksum"]
+
+
+def test_cli_fastq_oec_to_fasta(tmp_path):
+    """configs[0]-style plumbing: FASTQ + *.oec.zst batches -> FASTA, record set identical to the oracle's."""
+    from herro_b200 import cli
+    from tools import synth
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=13, min_len=4200)  # reads < W are never loaded (src/haec_io.rs:48)
+    descs = [None if i % 3 else f"ch={i} run=x" for i in range(rs.n)]
+    fq = str(tmp_path / "reads.fastq")
+    synth.write_fastq(rs, fq, descs)
+    synth.write_oec_batches(rs, str(tmp_path / "alns"), batch_size=11)
+    model = helpers.model_path(seed=3)
+    out = str(tmp_path / "out.fasta")
+    cli.main(["inference", "--read-alns", str(tmp_path / "alns"), "-m", model, "-b", "64", fq, out])
+    got = sorted(open(out, "rb").read().split(b">")[1:])
+    ora = helpers.run_oracle(rs, model, 4096, 64)
+    from herro_b200.api import fasta_records
+    want = []
+    for rid, segs in ora["segments"].items():
+        if segs:
+            d = descs[rid].encode() if descs[rid] is not None else None
+            want += fasta_records(rs.ids[rid].encode(), d, segs).split(b">")[1:]
+    assert got == sorted(want) and len(got) > 0
