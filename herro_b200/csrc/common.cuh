@@ -124,6 +124,30 @@ __device__ __forceinline__ uint32_t code_at(const uint64_t* __restrict__ w, uint
     return (uint32_t)(__ldg(w + (i >> 5)) >> ((i & 31u) << 1)) & 3u;
 }
 
+// 32 consecutive bases (2 bits each, base i at bits [2i, 2i+2)) starting at base index i of a packed read
+__device__ __forceinline__ uint64_t extract32(const uint64_t* __restrict__ w, uint32_t i) {
+    const uint32_t wi = i >> 5, sh = (i & 31u) << 1;
+    const uint64_t lo = __ldg(w + wi);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (__ldg(w + wi + 1) << (64u - sh));  // the store is padded by one word
+}
+// reverse the order of the 32 2-bit groups and complement them (A<->T, C<->G: code ^ 3)
+__device__ __forceinline__ uint64_t revcomp32(uint64_t v) {
+    uint64_t r = __brevll(v);
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    return ~r;
+}
+constexpr uint64_t LOW2 = 0x5555555555555555ull;
+// bit 2g set iff 2-bit group g of a and b differ, restricted to the first `len` groups (len >= 1)
+__device__ __forceinline__ uint64_t mismatch_groups(uint64_t a, uint64_t b, uint32_t len) {
+    const uint64_t d = a ^ b;
+    const uint64_t valid = len >= 32 ? LOW2 : (((1ull << (2u * len)) - 1ull) & LOW2);
+    return (d | (d >> 1)) & valid;
+}
+__device__ __forceinline__ uint64_t valid_groups(uint32_t len) {
+    return len >= 32 ? LOW2 : (((1ull << (2u * len)) - 1ull) & LOW2);
+}
+
 // View of the (strand-oriented) query slice of one overlap-window — src/features.rs:97-108,122-153
 struct QView {
     const uint64_t* words;
@@ -134,6 +158,13 @@ struct QView {
         return rev ? (code_at(words, qe - 1u - x) ^ 3u) : code_at(words, qs + x);
     }
     __device__ __forceinline__ uint8_t q(uint32_t x) const { return rev ? __ldg(qual + (qe - 1u - x)) : __ldg(qual + qs + x); }
+    // 32 oriented bases starting at oriented offset x (groups beyond the slice are unspecified)
+    __device__ __forceinline__ uint64_t chunk(uint32_t x) const {
+        if (!rev) return extract32(words, qs + x);
+        const uint32_t end = qe - x;  // exclusive end, original coordinates; oriented base g <-> position end-1-g
+        if (end >= 32) return revcomp32(extract32(words, end - 32));
+        return revcomp32(extract32(words, 0) << ((32u - end) * 2u));
+    }
 };
 
 __device__ __forceinline__ QView make_qview(const ReadStoreView& rs, const DevOverlap& ov, const DevOW& ow) {

@@ -907,7 +907,8 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
         max_len = std::max(max_len, seq_len[i]);
         if (!seq_words[i] || !qual[i]) return fail(ctx, HB_ERR_ARG, "null read");
     }
-    CK(ctx->d_words.ensure((woff[n_reads] + 1) * 8));
+    CK(ctx->d_words.ensure((woff[n_reads] + 8) * 8));  // padded: packed 32-base extraction may touch a few words past a read
+    CK(cudaMemset(ctx->d_words.as<uint64_t>() + woff[n_reads], 0, 8 * 8));
     CK(ctx->d_qual.ensure(qoff[n_reads] + 16));
     CK(ctx->d_word_off.ensure((n_reads + 1) * 8));
     CK(ctx->d_qual_off.ensure((n_reads + 1) * 8));

@@ -149,11 +149,15 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
         const QView qv = make_qview(b.rs, ov, ow);
         const uint64_t* __restrict__ tw = b.rs.words + b.rs.word_off[win.rid];
         uint32_t m = 0;
-        for (uint32_t k = 0; k < nops; k++) {
+        for (uint32_t k = lane; k < nops; k += 32) {  // one op per lane, 32 bases per step (packed 2-bit compare)
             const uint32_t kl = b.op_kl[ow.op_base + k];
             if ((kl & 3u) != OP_M) continue;
             const uint32_t eff = kl >> 2, t0 = win.tstart + b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
-            for (uint32_t j = lane; j < eff; j += 32) m += (code_at(tw, t0 + j) == qv.code(q0 + j)) ? 1u : 0u;
+            for (uint32_t i = 0; i < eff; i += 32) {
+                const uint32_t len = eff - i;
+                const uint64_t mm = mismatch_groups(extract32(tw, t0 + i), qv.chunk(q0 + i), len);
+                m += (len >= 32 ? 32u : len) - (uint32_t)__popcll(mm);
+            }
         }
         m = warp_sum(m);
         const uint32_t tot = sum_m + sum_i + sum_d;  // m + s + i + d
@@ -168,47 +172,34 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
     }
 }
 
-// Walk the (clipped) ops of one overlap-window with a whole warp.  fm(p, x) is called for
-// every matched base (window-relative target position p, oriented query offset x), fd(p)
-// for every deleted target position; lanes stride over the bases of an op.
-template <class FM, class FD>
-__device__ __forceinline__ void walk_md(const BatchView& b, uint32_t opb, uint32_t nops, int lane, FM fm, FD fd) {
-    for (uint32_t k = 0; k < nops; k++) {
-        const uint32_t kl = b.op_kl[opb + k];
-        const uint32_t kind = kl & 3u, eff = kl >> 2;
-        if (kind == OP_I) continue;
-        const uint32_t t0 = b.op_t[opb + k];
-        if (kind == OP_M) {
-            const uint32_t q0 = b.op_q[opb + k];
-            for (uint32_t j = lane; j < eff; j += 32) fm(t0 + j, q0 + j);
-        } else {
-            for (uint32_t j = lane; j < eff; j += 32) fd(t0 + j);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
 // K2: first pass of one window.  filter + stable sort by -accuracy (src/features.rs:376-409),
 //     first-pass supported base rows (get_supported on the [L, 1+max(n,30)] matrix, :438,
 //     restricted to base rows because only those enter the ranking, :481-491) and per-column
 //     match counts on them (:461-500).
-// ------------------------------------------------------------------------------------
+//
+//     Bit-parallel: a lane owns one CIGAR op and compares 32 packed bases per step (XOR of 2-bit
+//     words).  Per position only the exceptions are counted: coverage and gaps through difference
+//     arrays (+-1 at op boundaries, prefix-summed), mismatching bases individually; the count of
+//     the target's own allele is coverage - gaps - mismatches + 1.
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t W = b.W;
-    uint32_t* cnt_ac = (uint32_t*)smem_raw;
-    uint32_t* cnt_gt = cnt_ac + W;
-    uint32_t* cnt_gp = cnt_gt + W;
-    uint32_t* supbits = cnt_gp + W;                   // (W+31)/32 words
-    float* key = (float*)(supbits + ((W + 31) >> 5));  // MAX_COLS
-    uint32_t* cand = (uint32_t*)(key + MAX_COLS);      // MAX_COLS
-    __shared__ uint32_t s_n1, s_S, s_warp[8];
+    uint32_t* cnt_ac = (uint32_t*)smem_raw;           // mismatching A | C << 16 per position
+    uint32_t* cnt_gt = cnt_ac + W;                    // mismatching G | T << 16
+    uint32_t* dcg = cnt_gt + W;                       // [W+1] difference array: coverage (low 16) | gaps (high 16)
+    uint64_t* sup2 = (uint64_t*)(dcg + ((W + 2) & ~1u));  // first-pass supported positions, bit 2g of word p/32
+    uint64_t* s_t = sup2 + (W >> 5) + 2;              // target window, packed, word-aligned to the window start
+    float* key = (float*)(s_t + (W >> 5) + 2);        // MAX_COLS
+    uint32_t* cand = (uint32_t*)(key + MAX_COLS);     // MAX_COLS
+    __shared__ uint32_t s_n1, s_S, s_warp[8], s_carry;
 
     const uint32_t w = blockIdx.x;
     const DevWin win = b.win[w];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_in = win.ow_end - win.ow_begin;
-    if (tid == 0) { s_n1 = 0; s_S = 0; }
+    if (tid == 0) { s_n1 = 0; s_S = 0; s_carry = 0; }
     __syncthreads();
     if (n_in > MAX_COLS) {
         if (tid == 0) { atomicOr(&b.tgt_err[win.tgt], TERR_TOO_MANY_COLS); b.w_n1[w] = 0; b.w_S[w] = 0; }
@@ -243,57 +234,116 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
         }
         b.col_ow[win.ow_begin + r] = cand[i];
     }
-    for (uint32_t p = tid; p < W; p += 256) { cnt_ac[p] = 0; cnt_gt[p] = 0; cnt_gp[p] = 0; }
-    __syncthreads();  // also makes col_ow (global, written by this block) visible below
-
-    // ---- allele counts per target position over all columns
     const uint64_t* __restrict__ tw = b.rs.words + b.rs.word_off[win.rid];
+    for (uint32_t p = tid; p < W; p += 256) { cnt_ac[p] = 0; cnt_gt[p] = 0; dcg[p] = 0; }
+    if (tid == 0) dcg[W] = 0;
+    for (uint32_t i = tid; i < (W >> 5) + 2; i += 256) { sup2[i] = 0; s_t[i] = extract32(tw, win.tstart + i * 32); }
+    __syncthreads();
+
+    // ---- walk A: coverage / gap difference array and the mismatching bases of every column
     for (uint32_t c = warp; c < n1; c += 8) {
         const uint32_t owi = cand[c];  // order is irrelevant for counting
         const DevOW ow = b.ow[owi];
         const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
-        walk_md(b, ow.op_base, b.ow_nops[owi], lane,
-                [&](uint32_t p, uint32_t x) {
-                    const uint32_t cd = qv.code(x);
-                    atomicAdd((cd & 2u) ? &cnt_gt[p] : &cnt_ac[p], (cd & 1u) ? 0x10000u : 1u);
-                },
-                [&](uint32_t p) { atomicAdd(&cnt_gp[p], 1u); });
+        const uint32_t nops = b.ow_nops[owi];
+        if (lane == 0) {  // the column covers [p_first, p_end): every position there is an M or a D cell
+            atomicAdd(&dcg[ow.tstart - win.tstart], 1u);
+            atomicAdd(&dcg[b.ow_tend[owi]], 0xffffffffu);
+        }
+        for (uint32_t k = lane; k < nops; k += 32) {
+            const uint32_t kl = b.op_kl[ow.op_base + k];
+            const uint32_t kind = kl & 3u, eff = kl >> 2;
+            if (kind == OP_I) continue;
+            const uint32_t t0 = b.op_t[ow.op_base + k];
+            if (kind == OP_D) {
+                atomicAdd(&dcg[t0], 0x10000u);
+                atomicAdd(&dcg[t0 + eff], 0xffff0000u);
+                continue;
+            }
+            const uint32_t q0 = b.op_q[ow.op_base + k];
+            for (uint32_t i = 0; i < eff; i += 32) {
+                const uint32_t p = t0 + i;
+                // target chunk from the staged window: 32 bases at window-relative position p
+                const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
+                const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
+                const uint64_t qc = qv.chunk(q0 + i);
+                uint64_t mm = mismatch_groups(tc, qc, eff - i);
+                while (mm) {
+                    const int g2 = __ffsll((long long)mm) - 1;  // bit index 2g
+                    mm &= mm - 1;
+                    const uint32_t cd = (uint32_t)(qc >> g2) & 3u;
+                    atomicAdd((cd & 2u) ? &cnt_gt[p + (g2 >> 1)] : &cnt_ac[p + (g2 >> 1)], (cd & 1u) ? 0x10000u : 1u);
+                }
+            }
+        }
     }
     __syncthreads();
-    // ---- threshold: floor(0.1 * ncols) in f64 (src/features.rs:712), >= 2 alleles (:713-718)
+    // ---- prefix-sum the difference array -> coverage | gaps << 16 per position, then the thresholds:
+    //      floor(0.1 * ncols) in f64 (src/features.rs:712), >= 2 alleles (:713-718)
     const uint32_t ncols = 1u + (n1 > (uint32_t)TOP_K ? n1 : (uint32_t)TOP_K);
     const uint32_t thresh = (uint32_t)((double)ncols * 0.1);
     uint32_t S_local = 0;
-    for (uint32_t p0 = warp * 32; p0 < W; p0 += 256) {
-        const uint32_t p = p0 + lane;
+    for (uint32_t base = 0; base < W; base += 256) {
+        const uint32_t p = base + tid;
+        const uint32_t v = p < win.len ? dcg[p] : 0u;
+        const uint32_t inc = warp_incl_scan(v, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t off = s_carry;
+        for (int k = 0; k < warp; k++) off += s_warp[k];
+        const uint32_t cg = off + inc;  // inclusive: coverage and gaps AT position p
         bool sup = false;
         if (p < win.len) {
+            const uint32_t cov = cg & 0xffffu, gp = cg >> 16;
             uint32_t a = cnt_ac[p] & 0xffffu, c = cnt_ac[p] >> 16, g = cnt_gt[p] & 0xffffu, t = cnt_gt[p] >> 16;
-            const uint32_t gp = cnt_gp[p];
-            const uint32_t tc = code_at(tw, win.tstart + p);  // the target column's own base
-            a += (tc == 0); c += (tc == 1); g += (tc == 2); t += (tc == 3);
+            const uint32_t own = cov - gp - (a + c + g + t) + 1u;  // columns agreeing with the target + the target itself
+            const uint32_t tc = (uint32_t)(s_t[p >> 5] >> ((p & 31u) << 1)) & 3u;
+            a += (tc == 0) ? own : 0; c += (tc == 1) ? own : 0; g += (tc == 2) ? own : 0; t += (tc == 3) ? own : 0;
             const uint32_t ns = (a >= thresh) + (c >= thresh) + (g >= thresh) + (t >= thresh) + (gp >= thresh);
             sup = ns >= 2;
         }
         const uint32_t m = __ballot_sync(HB_FULL, sup);
-        if (lane == 0) { supbits[p0 >> 5] = m; S_local += __popc(m); }
+        if (lane == 0 && m) {
+            // spread the 32 flags to the even bits of a 64-bit word (bit 2g <-> position base + 32*warp + g)
+            uint64_t x = m;
+            x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+            x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+            x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+            x = (x | (x << 2)) & 0x3333333333333333ull;
+            x = (x | (x << 1)) & LOW2;
+            sup2[(base >> 5) + warp] = x;
+            S_local += __popc(m);
+        }
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_carry += t; }
+        __syncthreads();
     }
     if (lane == 0 && S_local) atomicAdd(&s_S, S_local);
     __syncthreads();
     const uint32_t S = s_S;
-    // ---- per-column matches on supported base rows; '.'/gap cells count as mismatches (H1),
+    // ---- walk B: per-column matches on supported base rows; '.'/gap cells count as mismatches (H1),
     //      hence d = S - n for every column of the window.
     if (S > 0) {
         for (uint32_t c = warp; c < n1; c += 8) {
             const uint32_t owi = cand[c];
             const DevOW ow = b.ow[owi];
             const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+            const uint32_t nops = b.ow_nops[owi];
             uint32_t n = 0;
-            walk_md(b, ow.op_base, b.ow_nops[owi], lane,
-                    [&](uint32_t p, uint32_t x) {
-                        if ((supbits[p >> 5] >> (p & 31)) & 1u) n += (qv.code(x) == code_at(tw, win.tstart + p)) ? 1u : 0u;
-                    },
-                    [&](uint32_t) {});
+            for (uint32_t k = lane; k < nops; k += 32) {
+                const uint32_t kl = b.op_kl[ow.op_base + k];
+                if ((kl & 3u) != OP_M) continue;
+                const uint32_t eff = kl >> 2, t0 = b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
+                for (uint32_t i = 0; i < eff; i += 32) {
+                    const uint32_t p = t0 + i;
+                    const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
+                    const uint64_t sc = sh ? ((sup2[wi] >> sh) | (sup2[wi + 1] << (64u - sh))) : sup2[wi];
+                    if (!sc) continue;
+                    const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
+                    const uint64_t mm = mismatch_groups(tc, qv.chunk(q0 + i), eff - i);
+                    n += (uint32_t)__popcll(sc & valid_groups(eff - i) & ~mm);
+                }
+            }
             n = warp_sum(n);
             if (lane == 0) {
                 atomicAdd(&b.ovl_n[ow.ovl], n);
@@ -482,13 +532,27 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
             // first p with row'(p) >= r1
             if (rm_s[i] >= r1 && (i == 0 || rm_s[i - 1] < r1)) s_phi = p_lo + i;
         }
-        // ---- initial fill: gap inside a column's aligned row range, '.' outside, '!' quals
-        for (uint32_t rr = warp; rr < (uint32_t)TR; rr += 8) {
+        // ---- initial fill, one thread per row: gap inside a column's aligned row range, '.' outside, '!' quals
+        for (uint32_t rr = tid; rr < (uint32_t)TR; rr += 256) {
             const uint32_t row = r0 + rr;
-            uint32_t tok = TOK_NONE;
-            if (row >= c_rs[lane] && row < c_re[lane]) tok = c_gap[lane];
-            t_tok[rr * ROW_BYTES + lane] = (uint8_t)tok;
-            t_q[rr * ROW_BYTES + lane] = QUAL_EMPTY;
+            uint32_t wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int c = i * 4 + e;
+                    const uint32_t tok = (row >= c_rs[c] && row < c_re[c]) ? c_gap[c] : TOK_NONE;
+                    x |= tok << (8 * e);
+                }
+                wv[i] = x;
+            }
+            uint4* tt = (uint4*)(t_tok + rr * ROW_BYTES);
+            uint4* tq = (uint4*)(t_q + rr * ROW_BYTES);
+            tt[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            tt[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+            tq[0] = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
+            tq[1] = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
         }
         __syncthreads();
         const uint32_t p_hi = s_phi;
@@ -553,33 +617,35 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
             }
         }
         __syncthreads();
-        // ---- per-row: second get_supported (src/features.rs:681-722 on [L',31]) and the
-        //      majority vote of consensus (src/consensus.rs:176-200).  warp per row, lane = column.
-        for (uint32_t rr = warp; rr < r1 - r0; rr += 8) {
-            const uint32_t tok = t_tok[rr * ROW_BYTES + lane];
-            const bool live = lane < R_COLS && tok < TOK_NONE;
-            const uint32_t cls = tok >= 5 ? tok - 5 : tok;  // BASES_UPPER_COUNTER / BASE_FORWARD
-            uint32_t cnt[5];
+        // ---- per-row: second get_supported (src/features.rs:681-722 on [L',31]) and the majority vote of
+        //      consensus (src/consensus.rs:176-200).  One thread per row; the 5 class counts come from
+        //      byte-parallel compares on the row's eight 32-bit words (column 31 is '.', never counted).
+        for (uint32_t rr = tid; rr < r1 - r0; rr += 256) {
+            const uint4 v0 = ((const uint4*)(t_tok + rr * ROW_BYTES))[0], v1 = ((const uint4*)(t_tok + rr * ROW_BYTES))[1];
+            const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t cnt[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-            for (int k = 0; k < 5; k++) cnt[k] = __popc(__ballot_sync(HB_FULL, live && cls == (uint32_t)k));
-            if (lane == 0) {
-                const uint32_t ns = (cnt[0] >= 3) + (cnt[1] >= 3) + (cnt[2] >= 3) + (cnt[3] >= 3) + (cnt[4] >= 3);
-                const bool sup = ns >= 2;
-                // two most common, stable on ties (A<C<G<T<*)
-                uint32_t b0 = 0;
+            for (int i = 0; i < 8; i++) {
+                const uint32_t x = wv[i];
+                const uint32_t cls = __vsub4(x, __vcmpgeu4(x, 0x05050505u) & 0x05050505u);  // BASES_UPPER_COUNTER / BASE_FORWARD
+                const uint32_t live = __vcmpltu4(x, 0x0a0a0a0au);                            // token < '.'
 #pragma unroll
-                for (int k = 1; k < 5; k++) if (cnt[k] > cnt[b0]) b0 = k;
-                uint32_t b1 = b0 == 0 ? 1 : 0;
-#pragma unroll
-                for (int k = 0; k < 5; k++) if ((uint32_t)k != b0 && (uint32_t)k != b1 && cnt[k] > cnt[b1]) b1 = k;
-                // (the loop above keeps the lowest index among equal counts because it only
-                //  replaces on strictly greater and starts from the lowest candidate)
-                const uint32_t tb = cls;  // lane 0 = target column, token 0..4
-                const uint32_t base = (cnt[b0] < 2 || (cnt[b0] == cnt[b1] && (b0 == tb || b1 == tb))) ? tb : b0;
-                const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
-                b.row_emit[rowbase + r0 + rr] = (uint8_t)(emit | (sup ? 0x80u : 0u));
-                sup_s[rr] = sup ? 1 : 0;
+                for (int k = 0; k < 5; k++) cnt[k] += __popc(__vcmpeq4(cls, 0x01010101u * (uint32_t)k) & live & 0x01010101u);
             }
+            const uint32_t ns = (cnt[0] >= 3) + (cnt[1] >= 3) + (cnt[2] >= 3) + (cnt[3] >= 3) + (cnt[4] >= 3);
+            const bool sup = ns >= 2;
+            // two most common, stable on ties (A<C<G<T<*)
+            uint32_t b0 = 0;
+#pragma unroll
+            for (int k = 1; k < 5; k++) if (cnt[k] > cnt[b0]) b0 = k;
+            uint32_t b1 = b0 == 0 ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) if ((uint32_t)k != b0 && (uint32_t)k != b1 && cnt[k] > cnt[b1]) b1 = k;
+            const uint32_t tb = wv[0] & 0xffu;  // target column, token 0..4
+            const uint32_t base = (cnt[b0] < 2 || (cnt[b0] == cnt[b1] && (b0 == tb || b1 == tb))) ? tb : b0;
+            const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
+            b.row_emit[rowbase + r0 + rr] = (uint8_t)(emit | (sup ? 0x80u : 0u));
+            sup_s[rr] = sup ? 1 : 0;
         }
         __syncthreads();
         // ---- ordered list of supported rows
@@ -693,7 +759,7 @@ __global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
 // ------------------------------------------------------------------------------------
 // launch wrappers (called from ctx.cu)
 // ------------------------------------------------------------------------------------
-size_t pass1_smem(uint32_t W) { return (size_t)W * 12 + ((W + 31) / 32) * 4 + MAX_COLS * 8 + 64; }
+size_t pass1_smem(uint32_t W) { return (size_t)W * 8 + (size_t)((W + 2) & ~1u) * 4 + 2 * ((W >> 5) + 2) * 8 + MAX_COLS * 8 + 64; }
 size_t pass2a_smem(uint32_t W) { return (size_t)((W + 2) & ~1u) * 4 + MAX_COLS * 8 + 64; }
 
 cudaError_t features_configure(uint32_t W) {
