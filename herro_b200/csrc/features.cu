@@ -477,14 +477,18 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ 
 //     memory, evaluate the second get_supported (thresh = floor(3.1) = 3) and the majority vote
 //     on the tile, and stream the tile to HBM with 16-byte stores.          (the pileup kernel)
 // ------------------------------------------------------------------------------------
-constexpr int TR = 512;  // rows per tile
+constexpr int TR = 1024;  // rows per tile
 
 __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
-    __shared__ __align__(16) uint8_t t_tok[TR * ROW_BYTES];
-    __shared__ __align__(16) uint8_t t_q[TR * ROW_BYTES];
-    __shared__ uint32_t rm_s[TR + 2];
-    __shared__ uint32_t pk_s[TR];
-    __shared__ uint8_t sup_s[TR];
+    // tile in shared memory, column-major ("planes"): plane c holds the TR tokens / quals of column c, so a column's
+    // consecutive rows are consecutive bytes (conflict-free scatter); rows are gathered per thread for the row-wise
+    // work and written to HBM row-major ([L',32], 32-byte rows).
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* p_tok = smem_raw;                    // [32][TR]
+    uint8_t* p_q = p_tok + 32 * TR;               // [32][TR]
+    uint32_t* rm_s = (uint32_t*)(p_q + 32 * TR);  // [TR + 2]
+    uint32_t* pk_s = rm_s + TR + 2;               // [TR]
+    uint8_t* sup_s = (uint8_t*)(pk_s + TR);       // [TR]
     __shared__ uint32_t c_ow[32], c_rs[32], c_re[32], c_gap[32];
     __shared__ uint32_t s_phi, s_warp[8], s_nsup;
 
@@ -532,27 +536,30 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
             // first p with row'(p) >= r1
             if (rm_s[i] >= r1 && (i == 0 || rm_s[i - 1] < r1)) s_phi = p_lo + i;
         }
-        // ---- initial fill, one thread per row: gap inside a column's aligned row range, '.' outside, '!' quals
-        for (uint32_t rr = tid; rr < (uint32_t)TR; rr += 256) {
-            const uint32_t row = r0 + rr;
-            uint32_t wv[8];
+        // ---- initial fill per plane, 16 rows per store: gap inside the column's aligned row range, '.' outside, '!' quals
+        for (uint32_t i = tid; i < 32u * (TR / 16); i += 256) {
+            const uint32_t c = i / (TR / 16), seg = i % (TR / 16);
+            const uint32_t row0 = r0 + seg * 16;
+            const uint32_t rs = c_rs[c], re = c_re[c], gap = c_gap[c];
+            uint32_t wv[4];
+            if (row0 >= rs && row0 + 16 <= re) {
+                wv[0] = wv[1] = wv[2] = wv[3] = gap * 0x01010101u;
+            } else if (row0 + 16 <= rs || row0 >= re) {
+                wv[0] = wv[1] = wv[2] = wv[3] = TOK_NONE * 0x01010101u;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                uint32_t x = 0;
+                for (int q4 = 0; q4 < 4; q4++) {
+                    uint32_t x = 0;
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int c = i * 4 + e;
-                    const uint32_t tok = (row >= c_rs[c] && row < c_re[c]) ? c_gap[c] : TOK_NONE;
-                    x |= tok << (8 * e);
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t row = row0 + q4 * 4 + e;
+                        x |= ((row >= rs && row < re) ? gap : TOK_NONE) << (8 * e);
+                    }
+                    wv[q4] = x;
                 }
-                wv[i] = x;
             }
-            uint4* tt = (uint4*)(t_tok + rr * ROW_BYTES);
-            uint4* tq = (uint4*)(t_q + rr * ROW_BYTES);
-            tt[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            tt[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-            tq[0] = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
-            tq[1] = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
+            *(uint4*)(p_tok + c * TR + seg * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            *(uint4*)(p_q + c * TR + seg * 16) = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
         }
         __syncthreads();
         const uint32_t p_hi = s_phi;
@@ -560,69 +567,115 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
         for (uint32_t p = p_lo + tid; p < p_hi; p += 256) {
             const uint32_t row = rm_s[p - p_lo], nxt = rm_s[p - p_lo + 1];
             if (row >= r0) {
-                t_tok[(row - r0) * ROW_BYTES] = (uint8_t)code_at(tw, win.tstart + p);
-                t_q[(row - r0) * ROW_BYTES] = __ldg(tq + p);
+                p_tok[row - r0] = (uint8_t)code_at(tw, win.tstart + p);
+                p_q[row - r0] = __ldg(tq + p);
             }
             for (uint32_t k = 0; row + k < nxt; k++) {
                 const uint32_t r = row + k;
                 if (r >= r0 && r < r1) pk_s[r - r0] = (p << 8) | (k & 0xffu);
             }
         }
-        // ---- overlap columns: scatter matched and inserted bases
+        // ---- overlap columns: a lane owns one op and expands its packed query bases (32 per 64-bit word) into the plane
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const uint32_t c = 1 + warp + 8 * s;
+        for (int s_ = 0; s_ < 4; s_++) {
+            const uint32_t c = 1 + warp + 8 * s_;
             if (c > nsel) continue;
             const uint32_t owi = c_ow[c];
             const DevOW ow = b.ow[owi];
             const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
             const uint32_t nops = b.ow_nops[owi];
             const uint32_t add = qv.rev ? 5u : 0u;
-            uint32_t k = cur[s];
-            bool advancing = true;
-            for (; k < nops; k++) {
-                const uint32_t kl = b.op_kl[ow.op_base + k];
-                const uint32_t kind = kl & 3u, eff = kl >> 2;
-                const uint32_t t0 = b.op_t[ow.op_base + k];
-                if (t0 > p_hi) break;
-                if (kind == OP_I) {
-                    const uint32_t pp = t0 - 1;  // insertion after target position pp
-                    if (pp >= p_lo && pp < p_hi) {
-                        const uint32_t q0 = b.op_q[ow.op_base + k];
-                        const uint32_t rb = rm_s[pp - p_lo] + 1;
-                        for (uint32_t j = lane; j < eff; j += 32) {
-                            const uint32_t r = rb + j;
-                            if (r >= r0 && r < r1) {
-                                t_tok[(r - r0) * ROW_BYTES + c] = (uint8_t)(qv.code(q0 + j) + add);
-                                t_q[(r - r0) * ROW_BYTES + c] = qv.q(q0 + j);
+            uint8_t* pt = p_tok + c * TR;
+            uint8_t* pq = p_q + c * TR;
+            uint32_t next_cur = 0xffffffffu;
+            for (uint32_t k0 = cur[s_]; k0 < nops; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                bool beyond = true;  // op starts after the tile's positions: nothing more for this column in this tile
+                if (k < nops) {
+                    const uint32_t kl = b.op_kl[ow.op_base + k];
+                    const uint32_t kind = kl & 3u, eff = kl >> 2;
+                    const uint32_t t0 = b.op_t[ow.op_base + k];
+                    beyond = t0 > p_hi;
+                    if (!beyond) {
+                        bool done;  // all rows of this op lie before the next tile
+                        if (kind == OP_I) {
+                            const uint32_t pp = t0 - 1;  // insertion after target position pp
+                            if (pp >= p_lo && pp < p_hi) {
+                                const uint32_t q0 = b.op_q[ow.op_base + k];
+                                const uint32_t rb = rm_s[pp - p_lo] + 1;
+                                for (uint32_t i = 0; i < eff; i += 32) {
+                                    const uint64_t qc = qv.chunk(q0 + i);
+                                    const uint32_t n = min(32u, eff - i);
+                                    for (uint32_t j = 0; j < n; j++) {
+                                        const uint32_t r = rb + i + j;
+                                        if (r >= r0 && r < r1) {
+                                            pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
+                                            pq[r - r0] = qv.q(q0 + i + j);
+                                        }
+                                    }
+                                }
                             }
-                        }
-                    }
-                    // done for later tiles iff its slots lie before position p_hi-1
-                    if (advancing && t0 < p_hi) cur[s] = k + 1; else advancing = false;
-                } else {
-                    const uint32_t lo = max(t0, p_lo), hi = min(t0 + eff, p_hi);
-                    if (kind == OP_M && lo < hi) {
-                        const uint32_t q0 = b.op_q[ow.op_base + k];
-                        for (uint32_t p = lo + lane; p < hi; p += 32) {
-                            const uint32_t r = rm_s[p - p_lo];
-                            if (r >= r0) {
-                                t_tok[(r - r0) * ROW_BYTES + c] = (uint8_t)(qv.code(q0 + (p - t0)) + add);
-                                t_q[(r - r0) * ROW_BYTES + c] = qv.q(q0 + (p - t0));
+                            done = t0 < p_hi;  // its slots lie before position p_hi-1
+                        } else {
+                            const uint32_t lo = max(t0, p_lo), hi = min(t0 + eff, p_hi);
+                            if (kind == OP_M && lo < hi) {
+                                const uint32_t q0 = b.op_q[ow.op_base + k];
+                                for (uint32_t p = lo; p < hi; p += 32) {
+                                    const uint64_t qc = qv.chunk(q0 + (p - t0));
+                                    const uint32_t n = min(32u, hi - p);
+                                    for (uint32_t j = 0; j < n; j++) {
+                                        const uint32_t r = rm_s[p + j - p_lo];
+                                        if (r >= r0) {
+                                            pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
+                                            pq[r - r0] = qv.q(q0 + (p + j - t0));
+                                        }
+                                    }
+                                }
                             }
+                            done = t0 + eff < p_hi;
                         }
+                        if (!done) next_cur = min(next_cur, k);
                     }
-                    if (advancing && t0 + eff < p_hi) cur[s] = k + 1; else advancing = false;
                 }
+                // ops are ordered by target position: stop once a whole group of 32 lies beyond the tile
+                const uint32_t nb = __ballot_sync(HB_FULL, beyond);
+                if (nb == HB_FULL) break;
             }
+            // first op that still has rows in later tiles (or the first op beyond this tile)
+            uint32_t nc = next_cur;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nc = min(nc, __shfl_xor_sync(HB_FULL, nc, o));
+            if (nc == 0xffffffffu) {
+                // every visited op is finished: continue from the first op that starts at/after p_hi - 1
+                uint32_t k = cur[s_];
+                // (rare path, warp-uniform scan)
+                while (k < nops) {
+                    const uint32_t kl = b.op_kl[ow.op_base + k];
+                    const uint32_t t0 = b.op_t[ow.op_base + k], eff = kl >> 2;
+                    const bool fin = ((kl & 3u) == OP_I) ? (t0 < p_hi) : (t0 + eff < p_hi);
+                    if (!fin) break;
+                    k++;
+                }
+                nc = k;
+            }
+            cur[s_] = nc;
         }
         __syncthreads();
-        // ---- per-row: second get_supported (src/features.rs:681-722 on [L',31]) and the majority vote of
-        //      consensus (src/consensus.rs:176-200).  One thread per row; the 5 class counts come from
-        //      byte-parallel compares on the row's eight 32-bit words (column 31 is '.', never counted).
+        // ---- per-row work, one thread per row: gather the row from the planes, second get_supported
+        //      (src/features.rs:681-722 on [L',31], thresh 3) and the majority vote of consensus
+        //      (src/consensus.rs:176-200) with byte-parallel class counts, row-major 32-byte stores to HBM.
         for (uint32_t rr = tid; rr < r1 - r0; rr += 256) {
-            const uint4 v0 = ((const uint4*)(t_tok + rr * ROW_BYTES))[0], v1 = ((const uint4*)(t_tok + rr * ROW_BYTES))[1];
-            const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t wv[8], qw[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t x = 0, y = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    x |= (uint32_t)p_tok[(i * 4 + e) * TR + rr] << (8 * e);
+                    y |= (uint32_t)p_q[(i * 4 + e) * TR + rr] << (8 * e);
+                }
+                wv[i] = x; qw[i] = y;
+            }
             uint32_t cnt[5] = {0, 0, 0, 0, 0};
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -646,6 +699,10 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
             const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
             b.row_emit[rowbase + r0 + rr] = (uint8_t)(emit | (sup ? 0x80u : 0u));
             sup_s[rr] = sup ? 1 : 0;
+            uint4* gb = (uint4*)(b.mat_bases + (rowbase + r0 + rr) * ROW_BYTES);
+            uint4* gq = (uint4*)(b.mat_quals + (rowbase + r0 + rr) * ROW_BYTES);
+            gb[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]); gb[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+            gq[0] = make_uint4(qw[0], qw[1], qw[2], qw[3]); gq[1] = make_uint4(qw[4], qw[5], qw[6], qw[7]);
         }
         __syncthreads();
         // ---- ordered list of supported rows
@@ -665,15 +722,6 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
             __syncthreads();
             if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_nsup += t; }
             __syncthreads();
-        }
-        // ---- stream the tile out (32 B per row, 16-byte stores)
-        {
-            const uint32_t n16 = (r1 - r0) * 2;
-            uint4* gb = (uint4*)(b.mat_bases + (rowbase + r0) * ROW_BYTES);
-            uint4* gq = (uint4*)(b.mat_quals + (rowbase + r0) * ROW_BYTES);
-            const uint4* sb = (const uint4*)t_tok;
-            const uint4* sq = (const uint4*)t_q;
-            for (uint32_t i = tid; i < n16; i += 256) { gb[i] = sb[i]; gq[i] = sq[i]; }
         }
         // next tile starts at the position whose rows straddle r1
         p_lo = (p_hi <= win.len && p_hi > 0 && rm_s[p_hi - p_lo] == r1) ? p_hi : p_hi - 1;
@@ -760,12 +808,15 @@ __global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
 // launch wrappers (called from ctx.cu)
 // ------------------------------------------------------------------------------------
 size_t pass1_smem(uint32_t W) { return (size_t)W * 8 + (size_t)((W + 2) & ~1u) * 4 + 2 * ((W >> 5) + 2) * 8 + MAX_COLS * 8 + 64; }
+size_t pass2b_smem() { return (size_t)64 * TR + (TR + 2) * 4 + TR * 4 + TR + 64; }
 size_t pass2a_smem(uint32_t W) { return (size_t)((W + 2) & ~1u) * 4 + MAX_COLS * 8 + 64; }
 
 cudaError_t features_configure(uint32_t W) {
     cudaError_t e = cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass1_smem(W));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_pass2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2a_smem(W));
+    e = cudaFuncSetAttribute(k_pass2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2a_smem(W));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pass2b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2b_smem());
 }
 
 int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
@@ -780,7 +831,7 @@ int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
     return n;
 }
 int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt) {
-    kt.begin(K_PILEUP); k_pass2b<<<b.n_win, 256, 0, st>>>(b); kt.end();
+    kt.begin(K_PILEUP); k_pass2b<<<b.n_win, 256, pass2b_smem(), st>>>(b); kt.end();
     return 1;
 }
 int launch_features_c1(const BatchView& b, cudaStream_t st, KTimer& kt) {
