@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ 
 //     memory, evaluate the second get_supported (thresh = floor(3.1) = 3) and the majority vote
 //     on the tile, and stream the tile to HBM with 16-byte stores.          (the pileup kernel)
 // ------------------------------------------------------------------------------------
-constexpr int TR = 1024;  // rows per tile
+constexpr int TR = 1024;     // rows per tile
+constexpr int QSTAGE = 1536;  // staged quality bytes per warp (>= TR + a straddling op)
 
 __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     // tile in shared memory, column-major ("planes"): plane c holds the TR tokens / quals of column c, so a column's
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     uint32_t* rm_s = (uint32_t*)(p_q + 32 * TR);  // [TR + 2]
     uint32_t* pk_s = rm_s + TR + 2;               // [TR]
     uint8_t* sup_s = (uint8_t*)(pk_s + TR);       // [TR]
+    uint8_t* q_stage = sup_s + TR;                // [8 warps][QSTAGE] staged quality bytes of the column being expanded
     __shared__ uint32_t c_ow[32], c_rs[32], c_re[32], c_gap[32];
     __shared__ uint32_t s_phi, s_warp[8], s_nsup;
 
@@ -519,8 +521,6 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     }
     if (tid == 0) s_nsup = 0;
 
-    // per-warp op cursors for the (up to 4) columns this warp owns: columns warp+1, warp+9, ...
-    uint32_t cur[4] = {0, 0, 0, 0};
     uint32_t p_lo = 0;
     __syncthreads();
 
@@ -575,90 +575,93 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                 if (r >= r0 && r < r1) pk_s[r - r0] = (p << 8) | (k & 0xffu);
             }
         }
-        // ---- overlap columns: a lane owns one op and expands its packed query bases (32 per 64-bit word) into the plane
-#pragma unroll
-        for (int s_ = 0; s_ < 4; s_++) {
-            const uint32_t c = 1 + warp + 8 * s_;
-            if (c > nsel) continue;
-            const uint32_t owi = c_ow[c];
-            const DevOW ow = b.ow[owi];
-            const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
-            const uint32_t nops = b.ow_nops[owi];
-            const uint32_t add = qv.rev ? 5u : 0u;
-            uint8_t* pt = p_tok + c * TR;
-            uint8_t* pq = p_q + c * TR;
-            uint32_t next_cur = 0xffffffffu;
-            for (uint32_t k0 = cur[s_]; k0 < nops; k0 += 32) {
-                const uint32_t k = k0 + lane;
-                bool beyond = true;  // op starts after the tile's positions: nothing more for this column in this tile
-                if (k < nops) {
-                    const uint32_t kl = b.op_kl[ow.op_base + k];
-                    const uint32_t kind = kl & 3u, eff = kl >> 2;
-                    const uint32_t t0 = b.op_t[ow.op_base + k];
-                    beyond = t0 > p_hi;
-                    if (!beyond) {
-                        bool done;  // all rows of this op lie before the next tile
+        // ---- overlap columns.  A warp owns a column; each lane owns an equal slice of the tile's target positions,
+        //      finds the op covering its first position by binary search and walks forward, expanding the packed query
+        //      bases (32 per 64-bit word) into the plane.  The column's quality bytes for the tile are staged through a
+        //      per-warp buffer with coalesced loads first (the L1 of this kernel is mostly carved out as shared memory).
+        {
+            const uint32_t npos = p_hi - p_lo;
+            const uint32_t seg = (npos + 31) / 32;
+            const uint32_t a = p_lo + lane * seg, bnd = min(p_hi, a + seg);  // this lane's positions [a, bnd)
+            uint8_t* qst = q_stage + warp * QSTAGE;
+#pragma unroll 1
+            for (int s_ = 0; s_ < 4; s_++) {
+                const uint32_t c = 1 + warp + 8 * s_;
+                if (c > nsel) break;
+                const uint32_t owi = c_ow[c];
+                const DevOW ow = b.ow[owi];
+                const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+                const uint32_t nops = b.ow_nops[owi];
+                const uint32_t* __restrict__ okl = b.op_kl + ow.op_base;
+                const uint32_t* __restrict__ opt = b.op_t + ow.op_base;
+                const uint32_t* __restrict__ opq = b.op_q + ow.op_base;
+                const uint32_t add = qv.rev ? 5u : 0u;
+                uint8_t* pt = p_tok + c * TR;
+                uint8_t* pq = p_q + c * TR;
+                // first op whose target span ends after p_lo (warp-uniform binary search on op_t)
+                uint32_t lo_k = 0, hi_k = nops;
+                while (lo_k < hi_k) {
+                    const uint32_t mid = (lo_k + hi_k) >> 1;
+                    if (opt[mid] < p_lo) lo_k = mid + 1; else hi_k = mid;
+                }
+                uint32_t k_first = lo_k;  // first op with op_t >= p_lo ...
+                if (k_first > 0) k_first--;  // ... and the one before it, which may straddle p_lo
+                const uint32_t qbase = k_first < nops ? opq[k_first] : 0;  // oriented offset where the staged window starts
+                const uint32_t qslice = ow.qend - ow.qstart;
+                const uint32_t qn = min((uint32_t)QSTAGE, qslice > qbase ? qslice - qbase : 0u);
+                for (uint32_t i = lane; i < qn; i += 32) qst[i] = qv.q(qbase + i);
+                __syncwarp();
+                auto qual_at = [&](uint32_t x) -> uint8_t { return (x - qbase < qn) ? qst[x - qbase] : qv.q(x); };
+                if (a < bnd) {
+                    // lane-local search: first op with op_t >= a, then step back to a straddling M/D op
+                    uint32_t l2 = k_first, h2 = nops;
+                    while (l2 < h2) {
+                        const uint32_t mid = (l2 + h2) >> 1;
+                        if (opt[mid] < a) l2 = mid + 1; else h2 = mid;
+                    }
+                    uint32_t k = l2;
+                    if (k > 0) {
+                        const uint32_t klp = okl[k - 1];
+                        if ((klp & 3u) != OP_I && opt[k - 1] + (klp >> 2) > a) k--;
+                    }
+                    for (; k < nops; k++) {
+                        const uint32_t kl = okl[k];
+                        const uint32_t kind = kl & 3u, eff = kl >> 2, t0 = opt[k];
+                        if (t0 > bnd) break;
                         if (kind == OP_I) {
-                            const uint32_t pp = t0 - 1;  // insertion after target position pp
-                            if (pp >= p_lo && pp < p_hi) {
-                                const uint32_t q0 = b.op_q[ow.op_base + k];
-                                const uint32_t rb = rm_s[pp - p_lo] + 1;
-                                for (uint32_t i = 0; i < eff; i += 32) {
-                                    const uint64_t qc = qv.chunk(q0 + i);
-                                    const uint32_t n = min(32u, eff - i);
-                                    for (uint32_t j = 0; j < n; j++) {
-                                        const uint32_t r = rb + i + j;
-                                        if (r >= r0 && r < r1) {
-                                            pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
-                                            pq[r - r0] = qv.q(q0 + i + j);
-                                        }
+                            const uint32_t pp = t0 - 1;  // insertion after target position pp: owned by the lane owning pp
+                            if (pp < a || pp >= bnd) continue;
+                            const uint32_t q0 = opq[k], rb = rm_s[pp - p_lo] + 1;
+                            for (uint32_t i = 0; i < eff; i += 32) {
+                                const uint64_t qc = qv.chunk(q0 + i);
+                                const uint32_t n = min(32u, eff - i);
+                                for (uint32_t j = 0; j < n; j++) {
+                                    const uint32_t r = rb + i + j;
+                                    if (r >= r0 && r < r1) {
+                                        pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
+                                        pq[r - r0] = qual_at(q0 + i + j);
                                     }
                                 }
                             }
-                            done = t0 < p_hi;  // its slots lie before position p_hi-1
-                        } else {
-                            const uint32_t lo = max(t0, p_lo), hi = min(t0 + eff, p_hi);
-                            if (kind == OP_M && lo < hi) {
-                                const uint32_t q0 = b.op_q[ow.op_base + k];
-                                for (uint32_t p = lo; p < hi; p += 32) {
-                                    const uint64_t qc = qv.chunk(q0 + (p - t0));
-                                    const uint32_t n = min(32u, hi - p);
-                                    for (uint32_t j = 0; j < n; j++) {
-                                        const uint32_t r = rm_s[p + j - p_lo];
-                                        if (r >= r0) {
-                                            pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
-                                            pq[r - r0] = qv.q(q0 + (p + j - t0));
-                                        }
+                        } else if (kind == OP_M) {
+                            const uint32_t lo = max(t0, a), hi = min(t0 + eff, bnd);
+                            const uint32_t q0 = opq[k];
+                            for (uint32_t p = lo; p < hi; p += 32) {
+                                const uint64_t qc = qv.chunk(q0 + (p - t0));
+                                const uint32_t n = min(32u, hi - p);
+                                for (uint32_t j = 0; j < n; j++) {
+                                    const uint32_t r = rm_s[p + j - p_lo];
+                                    if (r >= r0) {
+                                        pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
+                                        pq[r - r0] = qual_at(q0 + (p + j - t0));
                                     }
                                 }
                             }
-                            done = t0 + eff < p_hi;
                         }
-                        if (!done) next_cur = min(next_cur, k);
                     }
                 }
-                // ops are ordered by target position: stop once a whole group of 32 lies beyond the tile
-                const uint32_t nb = __ballot_sync(HB_FULL, beyond);
-                if (nb == HB_FULL) break;
+                __syncwarp();  // the staging buffer is reused by the next column
             }
-            // first op that still has rows in later tiles (or the first op beyond this tile)
-            uint32_t nc = next_cur;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nc = min(nc, __shfl_xor_sync(HB_FULL, nc, o));
-            if (nc == 0xffffffffu) {
-                // every visited op is finished: continue from the first op that starts at/after p_hi - 1
-                uint32_t k = cur[s_];
-                // (rare path, warp-uniform scan)
-                while (k < nops) {
-                    const uint32_t kl = b.op_kl[ow.op_base + k];
-                    const uint32_t t0 = b.op_t[ow.op_base + k], eff = kl >> 2;
-                    const bool fin = ((kl & 3u) == OP_I) ? (t0 < p_hi) : (t0 + eff < p_hi);
-                    if (!fin) break;
-                    k++;
-                }
-                nc = k;
-            }
-            cur[s_] = nc;
         }
         __syncthreads();
         // ---- per-row work, one thread per row: gather the row from the planes, second get_supported
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
 // launch wrappers (called from ctx.cu)
 // ------------------------------------------------------------------------------------
 size_t pass1_smem(uint32_t W) { return (size_t)W * 8 + (size_t)((W + 2) & ~1u) * 4 + 2 * ((W >> 5) + 2) * 8 + MAX_COLS * 8 + 64; }
-size_t pass2b_smem() { return (size_t)64 * TR + (TR + 2) * 4 + TR * 4 + TR + 64; }
+size_t pass2b_smem() { return (size_t)64 * TR + (TR + 2) * 4 + TR * 4 + TR + 8 * QSTAGE + 64; }
 size_t pass2a_smem(uint32_t W) { return (size_t)((W + 2) & ~1u) * 4 + MAX_COLS * 8 + 64; }
 
 cudaError_t features_configure(uint32_t W) {
