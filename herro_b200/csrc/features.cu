@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------
 constexpr int TR = 1024;     // rows per tile
 constexpr int QSTAGE = 1536;  // staged quality bytes per warp (>= TR + a straddling op)
+constexpr int OPCAP = 160;    // staged ops per warp and column-tile (falls back to global memory beyond)
 
 __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     // tile in shared memory, column-major ("planes"): plane c holds the TR tokens / quals of column c, so a column's
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     uint32_t* pk_s = rm_s + TR + 2;               // [TR]
     uint8_t* sup_s = (uint8_t*)(pk_s + TR);       // [TR]
     uint8_t* q_stage = sup_s + TR;                // [8 warps][QSTAGE] staged quality bytes of the column being expanded
+    uint32_t* op_stage = (uint32_t*)(q_stage + 8 * QSTAGE);  // [8 warps][3][OPCAP] staged ops of the column-tile
     __shared__ uint32_t c_ow[32], c_rs[32], c_re[32], c_gap[32];
     __shared__ uint32_t s_phi, s_warp[8], s_nsup;
 
@@ -591,10 +593,10 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                 const uint32_t owi = c_ow[c];
                 const DevOW ow = b.ow[owi];
                 const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
-                const uint32_t nops = b.ow_nops[owi];
-                const uint32_t* __restrict__ okl = b.op_kl + ow.op_base;
-                const uint32_t* __restrict__ opt = b.op_t + ow.op_base;
-                const uint32_t* __restrict__ opq = b.op_q + ow.op_base;
+                uint32_t nops = b.ow_nops[owi];
+                const uint32_t* okl = b.op_kl + ow.op_base;
+                const uint32_t* opt = b.op_t + ow.op_base;
+                const uint32_t* opq = b.op_q + ow.op_base;
                 const uint32_t add = qv.rev ? 5u : 0u;
                 uint8_t* pt = p_tok + c * TR;
                 uint8_t* pq = p_q + c * TR;
@@ -608,10 +610,32 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                 if (k_first > 0) k_first--;  // ... and the one before it, which may straddle p_lo
                 const uint32_t qbase = k_first < nops ? opq[k_first] : 0;  // oriented offset where the staged window starts
                 const uint32_t qslice = ow.qend - ow.qstart;
-                const uint32_t qn = min((uint32_t)QSTAGE, qslice > qbase ? qslice - qbase : 0u);
-                for (uint32_t i = lane; i < qn; i += 32) qst[i] = qv.q(qbase + i);
+                // ... and where it ends: the query offset of the first op that starts after the tile's positions
+                uint32_t lo_e = k_first, hi_e = nops;
+                while (lo_e < hi_e) {
+                    const uint32_t mid = (lo_e + hi_e) >> 1;
+                    if (opt[mid] <= p_hi) lo_e = mid + 1; else hi_e = mid;
+                }
+                const uint32_t qend_t = lo_e < nops ? opq[lo_e] : qslice;
+                const uint32_t qn = min((uint32_t)QSTAGE, qend_t > qbase ? qend_t - qbase : 0u);
+                for (uint32_t i0 = 0; i0 < qn; i0 += 256) {  // 8 independent byte loads in flight per lane
+                    uint8_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * 32 + lane; v[u] = i < qn ? qv.q(qbase + i) : 0; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * 32 + lane; if (i < qn) qst[i] = v[u]; }
+                }
+                // stage the ops that touch this tile (k_first .. lo_e) so that the lanes' searches and walks read shared memory
+                const uint32_t ne = min(nops, lo_e + 1) - k_first;
+                if (ne <= (uint32_t)OPCAP) {
+                    uint32_t* so = op_stage + warp * 3 * OPCAP;
+                    for (uint32_t i = lane; i < ne; i += 32) {
+                        so[i] = okl[k_first + i]; so[OPCAP + i] = opt[k_first + i]; so[2 * OPCAP + i] = opq[k_first + i];
+                    }
+                    okl = so - k_first; opt = so + OPCAP - k_first; opq = so + 2 * OPCAP - k_first;  // keep global op indices
+                    nops = k_first + ne;
+                }
                 __syncwarp();
-                auto qual_at = [&](uint32_t x) -> uint8_t { return (x - qbase < qn) ? qst[x - qbase] : qv.q(x); };
                 if (a < bnd) {
                     // lane-local search: first op with op_t >= a, then step back to a straddling M/D op
                     uint32_t l2 = k_first, h2 = nops;
@@ -624,40 +648,61 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                         const uint32_t klp = okl[k - 1];
                         if ((klp & 3u) != OP_I && opt[k - 1] + (klp >> 2) > a) k--;
                     }
-                    for (; k < nops; k++) {
-                        const uint32_t kl = okl[k];
-                        const uint32_t kind = kl & 3u, eff = kl >> 2, t0 = opt[k];
-                        if (t0 > bnd) break;
-                        if (kind == OP_I) {
-                            const uint32_t pp = t0 - 1;  // insertion after target position pp: owned by the lane owning pp
-                            if (pp < a || pp >= bnd) continue;
-                            const uint32_t q0 = opq[k], rb = rm_s[pp - p_lo] + 1;
-                            for (uint32_t i = 0; i < eff; i += 32) {
-                                const uint64_t qc = qv.chunk(q0 + i);
-                                const uint32_t n = min(32u, eff - i);
-                                for (uint32_t j = 0; j < n; j++) {
-                                    const uint32_t r = rb + i + j;
-                                    if (r >= r0 && r < r1) {
-                                        pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
-                                        pq[r - r0] = qual_at(q0 + i + j);
+                    // flat walk over this lane's positions: every lane runs the same ~seg iterations
+                    uint32_t kind = OP_D, op_end = a, xq = 0;  // current op: covers positions [.., op_end), next query offset xq
+                    uint64_t qc = 0;
+                    uint32_t cbase = 0xffffffffu;              // query offset of qc's first base
+                    for (uint32_t p = a; p < bnd; p++) {
+                        while (p >= op_end && k < nops) {      // advance to the op covering p, expanding insertions on the way
+                            const uint32_t kl = okl[k];
+                            const uint32_t kd = kl & 3u, eff = kl >> 2, t0 = opt[k];
+                            if (kd == OP_I) {
+                                const uint32_t pp = t0 - 1;    // insertion after position pp; ours iff a <= pp (pp < p holds here)
+                                if (pp >= a && pp < bnd) {
+                                    const uint32_t q0 = opq[k], rb = rm_s[pp - p_lo] + 1;
+                                    for (uint32_t j = 0; j < eff; j++) {
+                                        const uint32_t r = rb + j;
+                                        if (r >= r0 && r < r1) {
+                                            pt[r - r0] = (uint8_t)(qv.code(q0 + j) + add);
+                                            const uint32_t x = q0 + j;
+                                            pq[r - r0] = (x - qbase < qn) ? qst[x - qbase] : qv.q(x);
+                                        }
                                     }
                                 }
+                                k++;
+                                continue;
                             }
-                        } else if (kind == OP_M) {
-                            const uint32_t lo = max(t0, a), hi = min(t0 + eff, bnd);
-                            const uint32_t q0 = opq[k];
-                            for (uint32_t p = lo; p < hi; p += 32) {
-                                const uint64_t qc = qv.chunk(q0 + (p - t0));
-                                const uint32_t n = min(32u, hi - p);
-                                for (uint32_t j = 0; j < n; j++) {
-                                    const uint32_t r = rm_s[p + j - p_lo];
-                                    if (r >= r0) {
-                                        pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2 * j)) & 3u) + add);
-                                        pq[r - r0] = qual_at(q0 + (p + j - t0));
-                                    }
+                            if (t0 > p) { kind = OP_D; op_end = t0; break; }  // uncovered gap before the next op (cannot happen inside an overlap)
+                            kind = kd; op_end = t0 + eff; xq = opq[k] + (p - t0);
+                            k++;
+                        }
+                        if (p >= op_end) break;                // past the column's last op
+                        if (kind == OP_M) {
+                            if (xq - cbase >= 32u) { cbase = xq; qc = qv.chunk(cbase); }
+                            const uint32_t r = rm_s[p - p_lo];
+                            if (r >= r0) {
+                                pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2u * (xq - cbase))) & 3u) + add);
+                                pq[r - r0] = (xq - qbase < qn) ? qst[xq - qbase] : qv.q(xq);
+                            }
+                            xq++;
+                        }
+                    }
+                    // an insertion right after this lane's last position (op_t == bnd) belongs to this lane
+                    while (k < nops && opt[k] <= bnd) {
+                        const uint32_t kl = okl[k];
+                        if ((kl & 3u) == OP_I && opt[k] == bnd && bnd - 1 >= a) {
+                            const uint32_t eff = kl >> 2, q0 = opq[k], rb = rm_s[bnd - 1 - p_lo] + 1;
+                            for (uint32_t j = 0; j < eff; j++) {
+                                const uint32_t r = rb + j;
+                                if (r >= r0 && r < r1) {
+                                    pt[r - r0] = (uint8_t)(qv.code(q0 + j) + add);
+                                    const uint32_t x = q0 + j;
+                                    pq[r - r0] = (x - qbase < qn) ? qst[x - qbase] : qv.q(x);
                                 }
                             }
                         }
+                        if ((kl & 3u) != OP_I) break;
+                        k++;
                     }
                 }
                 __syncwarp();  // the staging buffer is reused by the next column
@@ -811,7 +856,7 @@ __global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
 // launch wrappers (called from ctx.cu)
 // ------------------------------------------------------------------------------------
 size_t pass1_smem(uint32_t W) { return (size_t)W * 8 + (size_t)((W + 2) & ~1u) * 4 + 2 * ((W >> 5) + 2) * 8 + MAX_COLS * 8 + 64; }
-size_t pass2b_smem() { return (size_t)64 * TR + (TR + 2) * 4 + TR * 4 + TR + 8 * QSTAGE + 64; }
+size_t pass2b_smem() { return (size_t)64 * TR + (TR + 2) * 4 + TR * 4 + TR + 8 * QSTAGE + 8 * 3 * OPCAP * 4 + 64; }
 size_t pass2a_smem(uint32_t W) { return (size_t)((W + 2) & ~1u) * 4 + MAX_COLS * 8 + 64; }
 
 cudaError_t features_configure(uint32_t W) {
