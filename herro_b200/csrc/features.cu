@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                     // flat walk over this lane's positions: every lane runs the same ~seg iterations
                     uint32_t kind = OP_D, op_end = a, xq = 0;  // current op: covers positions [.., op_end), next query offset xq
                     uint64_t qc = 0;
-                    uint32_t cbase = 0xffffffffu;              // query offset of qc's first base
+                    uint32_t cbase = 0;                        // query offset of qc's first base
+                    bool have_qc = false;
                     for (uint32_t p = a; p < bnd; p++) {
                         while (p >= op_end && k < nops) {      // advance to the op covering p, expanding insertions on the way
                             const uint32_t kl = okl[k];
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                         }
                         if (p >= op_end) break;                // past the column's last op
                         if (kind == OP_M) {
-                            if (xq - cbase >= 32u) { cbase = xq; qc = qv.chunk(cbase); }
+                            if (!have_qc || xq - cbase >= 32u) { cbase = xq; qc = qv.chunk(cbase); have_qc = true; }
                             const uint32_t r = rm_s[p - p_lo];
                             if (r >= r0) {
                                 pt[r - r0] = (uint8_t)(((uint32_t)(qc >> (2u * (xq - cbase))) & 3u) + add);
