@@ -477,9 +477,9 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ 
 //     memory, evaluate the second get_supported (thresh = floor(3.1) = 3) and the majority vote
 //     on the tile, and stream the tile to HBM with 16-byte stores.          (the pileup kernel)
 // ------------------------------------------------------------------------------------
-constexpr int TR = 1024;     // rows per tile
-constexpr int QSTAGE = 1536;  // staged quality bytes per warp (>= TR + a straddling op)
-constexpr int OPCAP = 160;    // staged ops per warp and column-tile (falls back to global memory beyond)
+constexpr int TR = 512;      // rows per tile
+constexpr int QSTAGE = 1024;  // staged quality bytes per warp (>= TR + a straddling op)
+constexpr int OPCAP = 96;     // staged ops per warp and column-tile (falls back to global memory beyond)
 
 __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     // tile in shared memory, column-major ("planes"): plane c holds the TR tokens / quals of column c, so a column's
