@@ -165,7 +165,9 @@ def main():
             return
         model, cfg = ensure_model()
         rs, _ = make_readset(args, 0)
-        per = max(2, args.cpu_sample // 2)
+        # bounded sample: the torch fp32 forward over whole [B,L,31] batches costs ~4 s per target read on the host,
+        # so a step is 2 target reads (1 when many steps are requested) and the whole run stays within a few minutes
+        per = 2 if (args.steps + args.warmup) <= 14 else 1
         need = (args.steps + args.warmup) * per
         tg = [t for t in range(rs.n)][:need]
         times, bases = [], 0
