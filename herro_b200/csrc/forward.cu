@@ -369,6 +369,7 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
     static const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid
     const bool fuse_ln = (C == 128) && !no_fuse;
+    static const bool no_fuse_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;  // debugging aid
     kt.begin(K_LAYERNORM);
     k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
     kt.end(); nl++;
@@ -389,9 +390,18 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
             gemm(wt, GEMM_OUT_F32_RES, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, C, st, kt); nl++;
             kt.begin(K_LAYERNORM); k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, ly.ln2_g, ly.ln2_b, (uint32_t)T, C); kt.end(); nl++;
         }
-        gemm(wt, GEMM_OUT_SPLIT_RELU, ws.Hhi, ws.Hlo, C, ly.s_1, ly.b1, nullptr, nullptr, 0, ws.Fhi, ws.Flo, F, T, F, C, st, kt); nl++;
         const float* ng = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_g : wt.lnf_g;
         const float* nb = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_b : wt.lnf_b;
+        if (fuse_ln && F == 512 && !no_fuse_ffn) {
+            // FFN1 -> ReLU -> FFN2 + residual + next LayerNorm in one kernel; the hidden activations stay on chip.
+            // In-place on H is safe: the tile's H rows are only overwritten after all of its MMAs have completed.
+            FfnArgs fa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_1.hi, (const __nv_bfloat16*)ly.s_1.lo,
+                       (const __nv_bfloat16*)ly.s_2.hi, (const __nv_bfloat16*)ly.s_2.lo, ly.b1, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo,
+                       (uint32_t)F, (uint32_t)(T / 128)};
+            kt.begin(K_GEMM); ffn_tc(fa, wt.num_sms, st); kt.end(); nl++;
+            continue;
+        }
+        gemm(wt, GEMM_OUT_SPLIT_RELU, ws.Hhi, ws.Hlo, C, ly.s_1, ly.b1, nullptr, nullptr, 0, ws.Fhi, ws.Flo, F, T, F, C, st, kt); nl++;
         if (fuse_ln) {
             gemm_ln(wt, ws.Fhi, ws.Flo, F, ly.s_2, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo, T, F, st, kt); nl++;
         } else {

@@ -52,6 +52,17 @@ struct GemmArgs {
     uint32_t m_tiles, n_chunks, k_blocks;  // M/128, N/128, K/64
     int mode;
 };
+struct FfnArgs {  // k_ffn_ws: fused FFN for C == 128, F == 512
+    const __nv_bfloat16 *Hhi, *Hlo;        // LayerNorm(X), split bf16, [T][128]
+    const __nv_bfloat16 *W1hi, *W1lo;      // [F][128]
+    const __nv_bfloat16 *W2hi, *W2lo;      // [128][F]
+    const float *b1, *b2;                  // [F], [128]
+    float* X;                              // residual stream [T][128], updated in place
+    const float *ln_g, *ln_b;              // LayerNorm that follows
+    __nv_bfloat16 *out_hi, *out_lo;        // LayerNorm(X_new), split bf16, [T][128]
+    uint32_t F, m_tiles;
+};
+cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st);
 struct StemArgs {  // k_stem_tc: the stem as a contraction over taps x 16 features (C == 128 only)
     const __nv_bfloat16 *Whi, *Wlo;  // W' [128][Kp], split bf16
     uint32_t Kp;                     // k_blocks * 64

@@ -312,6 +312,281 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused FFN for C == 128:   X += W2 · relu(W1 · H + b1) + b2 ;  H' = LayerNorm(X) (split bf16)
+// The hidden activations never leave the SM: per 128-token tile and per 128-wide hidden chunk c,
+//   F1(c): accF[c&1] = H · W1[c]^T           (tcgen05, H tile resident in shared memory)
+//   E1(c): relu(accF + b1[c]) -> split bf16 -> swizzled K-major tile A2 in shared memory
+//   F2(c): accO += A2 · W2[:, c]^T
+// and one final epilogue (residual, fp32 store, LayerNorm, split-bf16 store).  W1/W2 k-block tiles stream
+// through the cp.async ring in issue order F1(0) F1(1) F2(0) F1(2) F2(1) F1(3) F2(2) F2(3), so E1(c)
+// overlaps the MMAs of F1(c+1).  Saves writing and re-reading the [T, F] hidden tensor (4 KB per token and layer).
+// ------------------------------------------------------------------------------------------------
+constexpr int FFN_RING_BYTES = 2 * BN * 128;        // one W k-block tile, hi + lo: 32 KB
+constexpr int FFN_A_BYTES = 2 * 2 * BM * 128;       // a [128 x 128] operand as 2 k-blocks x (hi, lo): 64 KB
+
+// issue order of the 8 contractions of a tile: (is_F2, chunk)
+__device__ __forceinline__ void ffn_step(int i, int& is2, int& c) {
+    // 0:F1(0) 1:F1(1) 2:F2(0) 3:F1(2) 4:F2(1) 5:F1(3) 6:F2(2) 7:F2(3)
+    is2 = (0xD4 >> i) & 1;
+    c = (0xED84 >> (2 * i)) & 3;
+}
+constexpr int FFN_STAGES = 2;  // 2 x 64 KB operand tiles + 2 x 32 KB ring = 192 KB
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
+    uint8_t* sA2 = sA1 + FFN_A_BYTES;               // relu(hidden chunk) tile, same layout
+    uint8_t* ring = sA2 + FFN_A_BYTES;              // FFN_STAGES x FFN_RING_BYTES
+    __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full, a2_empty,
+        o_full[2], o_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a1_full, NUM_PROD); mbar_init(&a1_empty, 1);
+        mbar_init(&a2_full, NUM_EPI); mbar_init(&a2_empty, 1);
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], NUM_EPI);
+            mbar_init(&o_full[a], 1); mbar_init(&o_empty[a], NUM_EPI);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 512; i += NUM_THREADS) s_b1[i] = g.b1[i];
+    if (tid < BN) { s_b2[tid] = g.b2[tid]; s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    // TMEM columns: accF[0] 0..127, accF[1] 128..255, accO[0] 256..383, accO[1] 384..511
+
+    if (warp >= 4 && warp < 8) {
+        // =============================== producers ===============================
+        const int p = tid - 128;
+        uint32_t it_stage = 0, n_done = 0;
+        int pending = -1;
+        bool a1_pending = false;
+        for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+            const size_t m0 = (size_t)tile * BM;
+            // ---- H tile (resident for the whole tile): 2 k-blocks x (hi, lo)
+            mbar_wait(&a1_empty, (n_done & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int idx = i * 128 + p;                 // 2048 (row, chunk16) items of the [128 x 128] tile
+                const int r = idx >> 4, c16 = idx & 15, kb = c16 >> 3, c = c16 & 7;
+                const uint32_t off = (uint32_t)kb * (2 * BM * 128) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                const size_t ga = (m0 + r) * (size_t)BN + c16 * 8;
+                cp_async16(smem_u32(sA1) + off, g.Hhi + ga);
+                cp_async16(smem_u32(sA1) + BM * 128 + off, g.Hlo + ga);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            a1_pending = true;
+            // ---- the 16 weight k-block tiles of this tile, in MMA issue order
+            for (int st = 0; st < 8; st++) {
+                int is2, c;
+                ffn_step(st, is2, c);
+                for (int kb = 0; kb < 2; kb++, it_stage++) {
+                    const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
+                    const __nv_bfloat16* whi = is2 ? g.W2hi : g.W1hi;
+                    const __nv_bfloat16* wlo = is2 ? g.W2lo : g.W1lo;
+                    // F1(c): rows = hidden units c*128.., K = C;   F2(c): rows = outputs, K-columns = hidden units c*128..
+                    const size_t ld = is2 ? (size_t)g.F : (size_t)BN;
+                    const size_t row0 = is2 ? 0 : (size_t)c * 128, col0 = (is2 ? (size_t)c * 128 : 0) + (size_t)kb * BK;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int idx = i * 128 + p, r = idx >> 3, cc = idx & 7;
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
+                        const size_t gw = (row0 + r) * ld + col0 + cc * 8;
+                        cp_async16(sb + off, whi + gw);
+                        cp_async16(sb + BN * 128 + off, wlo + gw);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    // publish everything older than the group just committed
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (a1_pending) { mbar_arrive(&a1_full); a1_pending = false; }
+                    if (pending >= 0) mbar_arrive(&full_bar[pending]);
+                    pending = (int)s;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (a1_pending) mbar_arrive(&a1_full);
+        if (pending >= 0) mbar_arrive(&full_bar[pending]);
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            uint32_t it_stage = 0, n_done = 0, nf[2] = {0, 0}, na2 = 0;
+            const uint32_t a1b = smem_u32(sA1), a2b = smem_u32(sA2);
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                const uint32_t oacc = n_done & 1;
+                mbar_wait(&a1_full, n_done & 1);
+                for (int st = 0; st < 8; st++) {
+                    int is2, c;
+                    ffn_step(st, is2, c);
+                    uint32_t tmem_d, abase;
+                    if (!is2) {
+                        const uint32_t j = c & 1;
+                        mbar_wait(&f_empty[j], (nf[j] & 1) ^ 1);  // epilogue has drained accF[j]
+                        tmem_d = tmem_base + j * BN;
+                        abase = a1b;
+                    } else {
+                        mbar_wait(&a2_full, na2 & 1);             // E1(c) has written the hidden chunk
+                        if (c == 0) mbar_wait(&o_empty[oacc], ((n_done >> 1) & 1) ^ 1);
+                        tmem_d = tmem_base + 2 * BN + oacc * BN;
+                        abase = a2b;
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
+                        const uint64_t dAh = make_desc(abase + kb * (2 * BM * 128)), dAl = make_desc(abase + kb * (2 * BM * 128) + BM * 128);
+                        const uint64_t dBh = make_desc(sb), dBl = make_desc(sb + BN * 128);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            const uint32_t accum = (is2 ? (c | kb | k) : (kb | k)) ? 1u : 0u;
+                            mma_bf16(tmem_d, dAh + adv, dBh + adv, accum);
+                            mma_bf16(tmem_d, dAl + adv, dBh + adv, 1u);
+                            mma_bf16(tmem_d, dAh + adv, dBl + adv, 1u);
+                        }
+                        umma_commit(&empty_bar[s]);
+                    }
+                    if (!is2) {
+                        umma_commit(&f_full[c & 1]);
+                        nf[c & 1]++;
+                        if (c == 3) umma_commit(&a1_empty);       // H tile no longer needed
+                    } else {
+                        umma_commit(&a2_empty);
+                        na2++;
+                        if (c == 3) umma_commit(&o_full[oacc]);
+                    }
+                }
+            }
+        }
+    } else {
+        // =============================== epilogue ===============================
+        uint32_t n_done = 0, nf[2] = {0, 0}, na2 = 0;
+        for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+            const size_t row = (size_t)tile * BM + warp * 32 + lane;
+            const uint32_t r = warp * 32 + lane;
+            for (int c = 0; c < 4; c++) {
+                // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major, 2 k-blocks)
+                const uint32_t j = c & 1;
+                mbar_wait(&f_full[j], nf[j] & 1);
+                nf[j]++;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mbar_wait(&a2_empty, (na2 & 1) ^ 1);              // F2(c-1) has finished reading A2
+                na2++;
+                const uint32_t taddr = tmem_base + j * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+                    const float* bb = s_b1 + c * 128 + c0;
+                    const int kb = c0 >> 6;
+#pragma unroll
+                    for (int q8 = 0; q8 < 4; q8++) {              // 4 x 8 hidden units = 4 x 16-byte chunks of hi and of lo
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            const float a = fmaxf(__uint_as_float(v[q8 * 8 + e]) + bb[q8 * 8 + e], 0.f);
+                            const float b = fmaxf(__uint_as_float(v[q8 * 8 + e + 1]) + bb[q8 * 8 + e + 1], 0.f);
+                            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                            hi[e >> 1] = pack2(ah, bh);
+                            lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                        }
+                        const int cc = ((c0 & 63) >> 3) + q8;     // 16-byte chunk index inside the 128-byte k-block row
+                        const uint32_t off = (uint32_t)kb * (2 * BM * 128) + r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
+                        *(uint4*)(sA2 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *(uint4*)(sA2 + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&f_empty[j]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A2 -> tensor core
+                mbar_arrive(&a2_full);
+            }
+            // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16
+            const uint32_t oacc = n_done & 1;
+            mbar_wait(&o_full[oacc], (n_done >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ((uint32_t)(warp * 32) << 16);
+            float x[BN];
+            float* xrow = g.X + row * BN;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const float4 bv = *(const float4*)(s_b2 + c0 + jj);
+                    const float4 rr = *(const float4*)(xrow + c0 + jj);
+                    x[c0 + jj] = __uint_as_float(v[jj]) + bv.x + rr.x; x[c0 + jj + 1] = __uint_as_float(v[jj + 1]) + bv.y + rr.y;
+                    x[c0 + jj + 2] = __uint_as_float(v[jj + 2]) + bv.z + rr.z; x[c0 + jj + 3] = __uint_as_float(v[jj + 3]) + bv.w + rr.w;
+                    *(float4*)(xrow + c0 + jj) = make_float4(x[c0 + jj], x[c0 + jj + 1], x[c0 + jj + 2], x[c0 + jj + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&o_empty[oacc]);
+            float sum = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < BN; jj++) sum += x[jj];
+            const float mean = sum * (1.f / BN);
+            float var = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < BN; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
+            const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
+            uint4* ph = (uint4*)(g.out_hi + row * BN);
+            uint4* pl = (uint4*)(g.out_lo + row * BN);
+#pragma unroll
+            for (int jj = 0; jj < BN; jj += 8) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const float a = (x[jj + e] - mean) * rstd * s_lng[jj + e] + s_lnb[jj + e];
+                    const float b = (x[jj + e + 1] - mean) * rstd * s_lng[jj + e + 1] + s_lnb[jj + e + 1];
+                    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                    hi[e >> 1] = pack2(ah, bh);
+                    lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                }
+                ph[jj >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                pl[jj >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)2 * FFN_A_BYTES + (size_t)FFN_STAGES * FFN_RING_BYTES + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.m_tiles == 0) return cudaSuccess;
+    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), NUM_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stem on the tensor cores: Embedding(12,6) ++ qual -> Conv(7->C, k=(K,1)) is linear in the one-hot
 // token and in the quality value, so per read token it is a contraction over K' = taps x 16 features
 // (11 one-hot token slots, q_hi, q_lo, 3 zero) with W'[c][j*16+f] = tab[j][f][c] / wq[j][c].  The A
