@@ -77,12 +77,15 @@ __global__ void k_stem(BatchView b, FwdWeights wt, uint32_t n0, uint32_t npos, f
 __device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+__device__ __forceinline__ void split2f(float a, float b, uint32_t& hi, uint32_t& lo) {  // 2-wide converts (F2FP.PACK_AB)
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split4(const float (&y)[4], uint2& hi, uint2& lo) {
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) { h[e] = __float2bfloat16_rn(y[e]); l[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h[e])); }
-    hi = make_uint2(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]));
-    lo = make_uint2(pack_bf2(l[0], l[1]), pack_bf2(l[2], l[3]));
+    split2f(y[0], y[1], hi.x, lo.x);
+    split2f(y[2], y[3], hi.y, lo.y);
 }
 __global__ void k_layernorm(const float* __restrict__ X, __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo,
                             const float* __restrict__ g, const float* __restrict__ be, uint32_t rows, int C) {

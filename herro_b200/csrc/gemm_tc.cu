@@ -86,6 +86,15 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+// split two floats into packed bf16x2 hi and lo words with the 2-wide convert (F2FP.PACK_AB, full-rate ALU) instead of
+// four scalar F2F conversions: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -246,9 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                     for (int e = 0; e < 8; e += 2) {
                         const float a = (x[j + e] - mean) * rstd * s_lng[j + e] + s_lnb[j + e];
                         const float b = (x[j + e + 1] - mean) * rstd * s_lng[j + e + 1] + s_lnb[j + e + 1];
-                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                        hi[e >> 1] = pack2(ah, bh);
-                        lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                        split2(a, b, hi[e >> 1], lo[e >> 1]);
                     }
                     ph[j >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     pl[j >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -272,9 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const float a = fmaxf(o[j], 0.f), b = fmaxf(o[j + 1], 0.f);
-                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                        hi[j >> 1] = pack2(ah, bh);
-                        lo[j >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                        split2(a, b, hi[j >> 1], lo[j >> 1]);
                     }
                     uint4* ph = (uint4*)(g.out_hi + row * g.ldo + col);
                     uint4* pl = (uint4*)(g.out_lo + row * g.ldo + col);
@@ -503,9 +508,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
                         for (int e = 0; e < 8; e += 2) {
                             const float a = fmaxf(__uint_as_float(v[q8 * 8 + e]) + bb[q8 * 8 + e], 0.f);
                             const float b = fmaxf(__uint_as_float(v[q8 * 8 + e + 1]) + bb[q8 * 8 + e + 1], 0.f);
-                            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                            hi[e >> 1] = pack2(ah, bh);
-                            lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                            split2(a, b, hi[e >> 1], lo[e >> 1]);
                         }
                         const int cc = ((c0 & 63) >> 3) + q8;     // 16-byte chunk index inside the 128-byte k-block row
                         const uint32_t off = (uint32_t)kb * (2 * BM * 128) + r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
@@ -557,9 +560,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
                 for (int e = 0; e < 8; e += 2) {
                     const float a = (x[jj + e] - mean) * rstd * s_lng[jj + e] + s_lnb[jj + e];
                     const float b = (x[jj + e + 1] - mean) * rstd * s_lng[jj + e + 1] + s_lnb[jj + e + 1];
-                    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                    hi[e >> 1] = pack2(ah, bh);
-                    lo[e >> 1] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+                    split2(a, b, hi[e >> 1], lo[e >> 1]);
                 }
                 ph[jj >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 pl[jj >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
