@@ -200,8 +200,13 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV
         o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
     }
     __syncwarp();
-    const float scale = rsqrtf((float)DH);
-    float m = -INFINITY, l = 0.f;
+    // two passes: all 31 scores first (registers), then softmax weights and the weighted sum of V.  exp via ex2.approx
+    // (2 ulp) on log2e-prescaled scores: far inside the 1e-3 logit tolerance, and ~35 % fewer instructions than the
+    // online-softmax form (no running-max rescale of the accumulator).
+    const float scale_l2 = rsqrtf((float)DH) * 1.4426950408889634f;
+    float sc[R_COLS];
+    float m = -INFINITY;
+#pragma unroll
     for (int j = 0; j < R_COLS; j++) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -209,17 +214,19 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV
             const float4 k = *(const float4*)&sK[warp][j][d];
             s0 = fmaf(q[d], k.x, s0); s1 = fmaf(q[d + 1], k.y, s1); s2 = fmaf(q[d + 2], k.z, s2); s3 = fmaf(q[d + 3], k.w, s3);
         }
-        const float s = ((s0 + s1) + (s2 + s3)) * scale;
-        const float mn = fmaxf(m, s);
-        const float corr = expf(m - mn), p = expf(s - mn);
-        l = l * corr + p;
+        sc[j] = ((s0 + s1) + (s2 + s3)) * scale_l2;
+        m = fmaxf(m, sc[j]);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < R_COLS; j++) {
+        const float p = exp2f(sc[j] - m);
+        l += p;
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
             const float4 v = *(const float4*)&sV[warp][j][d];
-            o[d] = fmaf(p, v.x, o[d] * corr); o[d + 1] = fmaf(p, v.y, o[d + 1] * corr);
-            o[d + 2] = fmaf(p, v.z, o[d + 2] * corr); o[d + 3] = fmaf(p, v.w, o[d + 3] * corr);
+            o[d] = fmaf(p, v.x, o[d]); o[d + 1] = fmaf(p, v.y, o[d + 1]); o[d + 2] = fmaf(p, v.z, o[d + 2]); o[d + 3] = fmaf(p, v.w, o[d + 3]);
         }
-        m = mn;
     }
     const float inv = (lane < R_COLS) ? 1.f / l : 0.f;  // the pad token row is written as zeros
     const size_t ob = ((size_t)n * TOK_PER_POS + lane) * C + h * DH;
