@@ -30,7 +30,11 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int STAGE_BYTES = (2 * BM + 2 * BN) * 128;  // A hi/lo + W hi/lo tiles of one k-block: 64 KB
-constexpr int NUM_EPI = 128, NUM_PROD = 128, NUM_THREADS = 288;
+constexpr int NUM_EPI = 128, NUM_PROD = 128, NUM_THREADS = 288;  // k_stem_tc: warps 0-3 epilogue, 4-7 producers, 8 MMA
+// k_gemm_ws / k_ffn_ws: the epilogue is the critical path (4 warps could not keep up with the tensor pipe), so two
+// epilogue warpgroups split the 128 columns of an accumulator: warps 0-7 epilogue (warp & 3 = TMEM lane quadrant,
+// warp >> 2 = column half), warps 8-11 producers, warp 12 MMA
+constexpr int G_EPI = 256, G_THREADS = 416, G_PROD_WARP0 = 8, G_MMA_WARP = 12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,7 +115,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g) {
     extern __shared__ uint8_t smem_dyn[];
     // SWIZZLE_128B operands need 1024-byte alignment; the dynamic segment starts after the static one
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -120,15 +124,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
     // per-item bias chunk and the LayerNorm affine: read from shared memory in the epilogue (the L1 of this
     // kernel is almost entirely carved out for the operand ring, so repeated global reads would pay L2 latency)
     __shared__ __align__(16) float s_bias[2][BN], s_lng[BN], s_lnb[BN];
+    __shared__ float s_red[2][2][BM];  // [item parity][column half][row]: LayerNorm partial sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 8) {
+    if (warp == G_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], G_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,9 +144,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
     const uint32_t n_items = g.m_tiles * g.n_chunks;
     const uint32_t kbs = g.k_blocks;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= G_PROD_WARP0 && warp < G_MMA_WARP) {
         // =============================== producers ===============================
-        const int p = tid - 128;
+        const int p = tid - G_PROD_WARP0 * 32;
         uint32_t it_stage = 0;  // running k-block counter -> ring stage / parity
         int pending = -1;       // stage whose cp.asyncs are committed but not yet published
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full_bar[pending]);
         }
-    } else if (warp == 8) {
+    } else if (warp == G_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             uint32_t it_stage = 0, n_done = 0;
@@ -205,33 +210,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
             }
         }
     } else {
-        // =============================== epilogue ===============================
-        if (g.mode == GEMM_OUT_F32_RES_LN) { s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
+        // =============================== epilogue: 8 warps, 64 columns each =======================
+        const int wq = warp & 3, eh = warp >> 2;  // TMEM lane quadrant, column half
+        const int ch = eh * 64;                   // first of this thread's 64 columns inside the 128-wide item
+        if (g.mode == GEMM_OUT_F32_RES_LN && tid < BN) { s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t m0 = (item / g.n_chunks) * BM, n0 = (item % g.n_chunks) * BN;
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
-            s_bias[acc][tid] = g.bias[n0 + tid];     // the previous user of this slot finished 2 items ago
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // epilogue warps only
-            const float* sb = s_bias[acc];
+            if (tid < BN) s_bias[acc][tid] = g.bias[n0 + tid];  // the previous user of this slot finished 2 items ago
+            asm volatile("bar.sync 2, 256;" ::: "memory");       // epilogue warps only
+            const float* sb = s_bias[acc] + ch;
             mbar_wait(&tfull_bar[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const size_t row = (size_t)m0 + warp * 32 + lane;
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
+            const uint32_t r = wq * 32 + lane;
+            const size_t row = (size_t)m0 + r;
+            const uint32_t taddr = tmem_base + acc * BN + ch + ((uint32_t)(wq * 32) << 16);
             if (g.mode == GEMM_OUT_F32_RES_LN) {
-                // the thread owns its whole 128-wide row: residual add, fp32 store, LayerNorm, split-bf16 store
-                float x[BN];
-                float* xrow = g.out + row * g.ldc;
+                // residual add + fp32 store of this thread's half row, then LayerNorm of the whole row with the
+                // partial sums exchanged with the thread that owns the other half
+                float x[64];
+                float* xrow = g.out + row * g.ldc + ch;
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = *(const float4*)(sb + c0 + j);
-                        const float4 r = *(const float4*)(xrow + c0 + j);
-                        x[c0 + j] = __uint_as_float(v[j]) + bv.x + r.x; x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bv.y + r.y;
-                        x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bv.z + r.z; x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bv.w + r.w;
+                        const float4 rr = *(const float4*)(xrow + c0 + j);
+                        x[c0 + j] = __uint_as_float(v[j]) + bv.x + rr.x; x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bv.y + rr.y;
+                        x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bv.z + rr.z; x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bv.w + rr.w;
                         *(float4*)(xrow + c0 + j) = make_float4(x[c0 + j], x[c0 + j + 1], x[c0 + j + 2], x[c0 + j + 3]);
                     }
                 }
@@ -240,21 +249,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                 mbar_arrive(&tempty_bar[acc]);
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < BN; j++) sum += x[j];
-                const float mean = sum * (1.f / BN);
+                for (int j = 0; j < 64; j++) sum += x[j];
+                s_red[acc][eh][r] = sum;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float mean = (s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN);
                 float var = 0.f;
 #pragma unroll
-                for (int j = 0; j < BN; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
-                const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
-                uint4* ph = (uint4*)(g.out_hi + row * g.ldo);
-                uint4* pl = (uint4*)(g.out_lo + row * g.ldo);
+                for (int j = 0; j < 64; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // both halves have read the sums
+                s_red[acc][eh][r] = var;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float rstd = rsqrtf((s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN) + 1e-5f);
+                uint4* ph = (uint4*)(g.out_hi + row * g.ldo + ch);
+                uint4* pl = (uint4*)(g.out_lo + row * g.ldo + ch);
 #pragma unroll
-                for (int j = 0; j < BN; j += 8) {
+                for (int j = 0; j < 64; j += 8) {
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
-                        const float a = (x[j + e] - mean) * rstd * s_lng[j + e] + s_lnb[j + e];
-                        const float b = (x[j + e + 1] - mean) * rstd * s_lng[j + e + 1] + s_lnb[j + e + 1];
+                        const float a = (x[j + e] - mean) * rstd * s_lng[ch + j + e] + s_lnb[ch + j + e];
+                        const float b = (x[j + e + 1] - mean) * rstd * s_lng[ch + j + e + 1] + s_lnb[ch + j + e + 1];
                         split2(a, b, hi[e >> 1], lo[e >> 1]);
                     }
                     ph[j >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -263,10 +277,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                 continue;
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
-                const int col = (int)n0 + c0;
+                const int col = (int)n0 + ch + c0;
                 float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -277,10 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                 if (g.mode == GEMM_OUT_SPLIT_RELU) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float a = fmaxf(o[j], 0.f), b = fmaxf(o[j + 1], 0.f);
-                        split2(a, b, hi[j >> 1], lo[j >> 1]);
-                    }
+                    for (int j = 0; j < 32; j += 2) split2(fmaxf(o[j], 0.f), fmaxf(o[j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
                     uint4* ph = (uint4*)(g.out_hi + row * g.ldo + col);
                     uint4* pl = (uint4*)(g.out_lo + row * g.ldo + col);
 #pragma unroll
@@ -294,8 +305,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
                         const float* res = g.res + row * g.ldc + col;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 r = *(const float4*)(res + j);
-                            o[j] += r.x; o[j + 1] += r.y; o[j + 2] += r.z; o[j + 3] += r.w;
+                            const float4 rr = *(const float4*)(res + j);
+                            o[j] += rr.x; o[j + 1] += rr.y; o[j + 2] += rr.z; o[j + 3] += rr.w;
                         }
                     } else if (g.mode == GEMM_OUT_F32_RELU) {
 #pragma unroll
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_ws(GemmArgs g) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == G_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
@@ -337,7 +348,7 @@ __device__ __forceinline__ void ffn_step(int i, int& is2, int& c) {
 }
 constexpr int FFN_STAGES = 2;  // 2 x 64 KB operand tiles + 2 x 32 KB ring = 192 KB
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
+__global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
@@ -347,23 +358,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
         o_full[2], o_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN];
+    __shared__ float s_red[2][2][BM];  // [tile parity][column half][row]: LayerNorm partial sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 8) {
+    if (warp == G_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
         mbar_init(&a1_full, NUM_PROD); mbar_init(&a1_empty, 1);
-        mbar_init(&a2_full, NUM_EPI); mbar_init(&a2_empty, 1);
+        mbar_init(&a2_full, G_EPI); mbar_init(&a2_empty, 1);
         for (int a = 0; a < 2; a++) {
-            mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], NUM_EPI);
-            mbar_init(&o_full[a], 1); mbar_init(&o_empty[a], NUM_EPI);
+            mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], G_EPI);
+            mbar_init(&o_full[a], 1); mbar_init(&o_empty[a], G_EPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 512; i += NUM_THREADS) s_b1[i] = g.b1[i];
+    for (int i = tid; i < 512; i += G_THREADS) s_b1[i] = g.b1[i];
     if (tid < BN) { s_b2[tid] = g.b2[tid]; s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -371,9 +383,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
     const uint32_t tmem_base = tmem_base_s;
     // TMEM columns: accF[0] 0..127, accF[1] 128..255, accO[0] 256..383, accO[1] 384..511
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= G_PROD_WARP0 && warp < G_MMA_WARP) {
         // =============================== producers ===============================
-        const int p = tid - 128;
+        const int p = tid - G_PROD_WARP0 * 32;
         uint32_t it_stage = 0, n_done = 0;
         int pending = -1;
         bool a1_pending = false;
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (a1_pending) mbar_arrive(&a1_full);
         if (pending >= 0) mbar_arrive(&full_bar[pending]);
-    } else if (warp == 8) {
+    } else if (warp == G_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             uint32_t it_stage = 0, n_done = 0, nf[2] = {0, 0}, na2 = 0;
@@ -481,39 +493,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
             }
         }
     } else {
-        // =============================== epilogue ===============================
+        // =============================== epilogue: 8 warps, 64 columns each =======================
+        const int wq = warp & 3, eh = warp >> 2;  // TMEM lane quadrant, column half (= k-block of the A2 tile)
+        const int ch = eh * 64;
         uint32_t n_done = 0, nf[2] = {0, 0}, na2 = 0;
         for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
-            const size_t row = (size_t)tile * BM + warp * 32 + lane;
-            const uint32_t r = warp * 32 + lane;
+            const uint32_t r = wq * 32 + lane;
+            const size_t row = (size_t)tile * BM + r;
             for (int c = 0; c < 4; c++) {
-                // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major, 2 k-blocks)
+                // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major; this thread's 64 columns = k-block eh)
                 const uint32_t j = c & 1;
                 mbar_wait(&f_full[j], nf[j] & 1);
                 nf[j]++;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 mbar_wait(&a2_empty, (na2 & 1) ^ 1);              // F2(c-1) has finished reading A2
                 na2++;
-                const uint32_t taddr = tmem_base + j * BN + ((uint32_t)(warp * 32) << 16);
+                const uint32_t taddr = tmem_base + j * BN + ch + ((uint32_t)(wq * 32) << 16);
+                uint8_t* a2row = sA2 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);
-                    const float* bb = s_b1 + c * 128 + c0;
-                    const int kb = c0 >> 6;
+                    const float* bb = s_b1 + c * 128 + ch + c0;
 #pragma unroll
                     for (int q8 = 0; q8 < 4; q8++) {              // 4 x 8 hidden units = 4 x 16-byte chunks of hi and of lo
                         uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2) {
-                            const float a = fmaxf(__uint_as_float(v[q8 * 8 + e]) + bb[q8 * 8 + e], 0.f);
-                            const float b = fmaxf(__uint_as_float(v[q8 * 8 + e + 1]) + bb[q8 * 8 + e + 1], 0.f);
-                            split2(a, b, hi[e >> 1], lo[e >> 1]);
-                        }
-                        const int cc = ((c0 & 63) >> 3) + q8;     // 16-byte chunk index inside the 128-byte k-block row
-                        const uint32_t off = (uint32_t)kb * (2 * BM * 128) + r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
-                        *(uint4*)(sA2 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *(uint4*)(sA2 + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        for (int e = 0; e < 8; e += 2)
+                            split2(fmaxf(__uint_as_float(v[q8 * 8 + e]) + bb[q8 * 8 + e], 0.f),
+                                   fmaxf(__uint_as_float(v[q8 * 8 + e + 1]) + bb[q8 * 8 + e + 1], 0.f), hi[e >> 1], lo[e >> 1]);
+                        const int cc = (c0 >> 3) + q8;            // 16-byte chunk index inside the 128-byte k-block row
+                        const uint32_t off = (uint32_t)((cc ^ (r & 7)) << 4);
+                        *(uint4*)(a2row + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *(uint4*)(a2row + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -521,20 +533,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A2 -> tensor core
                 mbar_arrive(&a2_full);
             }
-            // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16
+            // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16 (partial sums exchanged between the halves)
             const uint32_t oacc = n_done & 1;
             mbar_wait(&o_full[oacc], (n_done >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ((uint32_t)(warp * 32) << 16);
-            float x[BN];
-            float* xrow = g.X + row * BN;
+            const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ch + ((uint32_t)(wq * 32) << 16);
+            float x[64];
+            float* xrow = g.X + row * BN + ch;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 bv = *(const float4*)(s_b2 + c0 + jj);
+                    const float4 bv = *(const float4*)(s_b2 + ch + c0 + jj);
                     const float4 rr = *(const float4*)(xrow + c0 + jj);
                     x[c0 + jj] = __uint_as_float(v[jj]) + bv.x + rr.x; x[c0 + jj + 1] = __uint_as_float(v[jj + 1]) + bv.y + rr.y;
                     x[c0 + jj + 2] = __uint_as_float(v[jj + 2]) + bv.z + rr.z; x[c0 + jj + 3] = __uint_as_float(v[jj + 3]) + bv.w + rr.w;
@@ -545,21 +557,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
             mbar_arrive(&o_empty[oacc]);
             float sum = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < BN; jj++) sum += x[jj];
-            const float mean = sum * (1.f / BN);
+            for (int jj = 0; jj < 64; jj++) sum += x[jj];
+            s_red[oacc][eh][r] = sum;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const float mean = (s_red[oacc][0][r] + s_red[oacc][1][r]) * (1.f / BN);
             float var = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < BN; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
-            const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
-            uint4* ph = (uint4*)(g.out_hi + row * BN);
-            uint4* pl = (uint4*)(g.out_lo + row * BN);
+            for (int jj = 0; jj < 64; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            s_red[oacc][eh][r] = var;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const float rstd = rsqrtf((s_red[oacc][0][r] + s_red[oacc][1][r]) * (1.f / BN) + 1e-5f);
+            uint4* ph = (uint4*)(g.out_hi + row * BN + ch);
+            uint4* pl = (uint4*)(g.out_lo + row * BN + ch);
 #pragma unroll
-            for (int jj = 0; jj < BN; jj += 8) {
+            for (int jj = 0; jj < 64; jj += 8) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                    const float a = (x[jj + e] - mean) * rstd * s_lng[jj + e] + s_lnb[jj + e];
-                    const float b = (x[jj + e + 1] - mean) * rstd * s_lng[jj + e + 1] + s_lnb[jj + e + 1];
+                    const float a = (x[jj + e] - mean) * rstd * s_lng[ch + jj + e] + s_lnb[ch + jj + e];
+                    const float b = (x[jj + e + 1] - mean) * rstd * s_lng[ch + jj + e + 1] + s_lnb[ch + jj + e + 1];
                     split2(a, b, hi[e >> 1], lo[e >> 1]);
                 }
                 ph[jj >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -569,7 +586,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_ffn_ws(FfnArgs g) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == G_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
@@ -583,7 +600,7 @@ cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
         configured = true;
     }
     if (a.m_tiles == 0) return cudaSuccess;
-    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), NUM_THREADS, smem, st>>>(a);
+    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -819,7 +836,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
     const uint32_t items = a.m_tiles * a.n_chunks;
     if (items == 0) return cudaSuccess;
     const unsigned grid = (unsigned)std::min<uint32_t>(items, (uint32_t)num_sms);
-    k_gemm_ws<<<grid, NUM_THREADS, smem, st>>>(a);
+    k_gemm_ws<<<grid, G_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
