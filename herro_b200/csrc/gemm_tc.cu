@@ -19,6 +19,7 @@
 // Two TMEM accumulators (2 x 128 columns) let the epilogue of item i overlap the MMAs of i+1.
 // Work items (m_tile, n_chunk) are dealt round-robin so CTAs working on the same m_tile share
 // its A tile in L2.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -33,8 +34,8 @@ constexpr int STAGE_BYTES = (2 * BM + 2 * BN) * 128;  // A hi/lo + W hi/lo tiles
 constexpr int NUM_EPI = 128, NUM_PROD = 128, NUM_THREADS = 288;  // k_stem_tc: warps 0-3 epilogue, 4-7 producers, 8 MMA
 // k_gemm_ws / k_ffn_ws: the epilogue is the critical path (4 warps could not keep up with the tensor pipe), so two
 // epilogue warpgroups split the 128 columns of an accumulator: warps 0-7 epilogue (warp & 3 = TMEM lane quadrant,
-// warp >> 2 = column half), warps 8-11 producers, warp 12 MMA
-constexpr int G_EPI = 256, G_THREADS = 416, G_PROD_WARP0 = 8, G_MMA_WARP = 12;
+// warp >> 2 = column half), warp 8 TMA producer, warp 9 MMA
+constexpr int G_EPI = 256, G_THREADS = 320, G_PROD_WARP = 8, G_MMA_WARP = 9;  // operands arrive by TMA: one producer lane
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +60,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     // arrives once all tcgen05.mma issued so far by this thread have completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one thread copies a [128 rows x 64 bf16] box of a 2-D tensor into a SWIZZLE_128B shared-memory tile
+// (the layout the UMMA descriptors expect) and completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c_inner, int c_row) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
+                 : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -115,7 +126,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g) {
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __grid_constant__ CUtensorMap tmAhi,
+                                                         const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmWhi,
+                                                         const __grid_constant__ CUtensorMap tmWlo) {
     extern __shared__ uint8_t smem_dyn[];
     // SWIZZLE_128B operands need 1024-byte alignment; the dynamic segment starts after the static one
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], G_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -144,42 +157,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g) {
     const uint32_t n_items = g.m_tiles * g.n_chunks;
     const uint32_t kbs = g.k_blocks;
 
-    if (warp >= G_PROD_WARP0 && warp < G_MMA_WARP) {
-        // =============================== producers ===============================
-        const int p = tid - G_PROD_WARP0 * 32;
-        uint32_t it_stage = 0;  // running k-block counter -> ring stage / parity
-        int pending = -1;       // stage whose cp.asyncs are committed but not yet published
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const uint32_t m0 = (item / g.n_chunks) * BM, n0 = (item % g.n_chunks) * BN;
-            for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
-                const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const uint32_t sb = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const size_t k0 = (size_t)kb * BK;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int idx = i * 128 + p, r = idx >> 3, c = idx & 7;
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                    const size_t ga = (size_t)(m0 + r) * g.lda + k0 + c * 8;
-                    const size_t gw = (size_t)(n0 + r) * g.K + k0 + c * 8;
-                    cp_async16(sb + off, g.Ahi + ga);
-                    cp_async16(sb + BM * 128 + off, g.Alo + ga);
-                    cp_async16(sb + 2 * BM * 128 + off, g.Whi + gw);
-                    cp_async16(sb + 2 * BM * 128 + BN * 128 + off, g.Wlo + gw);
+    if (warp == G_PROD_WARP) {
+        // =============================== producer: one lane issues the TMA copies ===============================
+        if (lane == 0) {
+            uint32_t it_stage = 0;  // running k-block counter -> ring stage / parity
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int m0 = (int)((item / g.n_chunks) * BM), n0 = (int)((item % g.n_chunks) * BN);
+                for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
+                    const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t sb = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    const int k0 = (int)(kb * BK);
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(sb, &tmAhi, &full_bar[s], k0, m0);
+                    tma_load_2d(sb + BM * 128, &tmAlo, &full_bar[s], k0, m0);
+                    tma_load_2d(sb + 2 * BM * 128, &tmWhi, &full_bar[s], k0, n0);
+                    tma_load_2d(sb + 2 * BM * 128 + BN * 128, &tmWlo, &full_bar[s], k0, n0);
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (pending >= 0) {
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
-                    mbar_arrive(&full_bar[pending]);
-                }
-                pending = (int)s;
             }
-        }
-        if (pending >= 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full_bar[pending]);
         }
     } else if (warp == G_MMA_WARP) {
         // =============================== MMA issuer ===============================
@@ -348,7 +343,10 @@ __device__ __forceinline__ void ffn_step(int i, int& is2, int& c) {
 }
 constexpr int FFN_STAGES = 2;  // 2 x 64 KB operand tiles + 2 x 32 KB ring = 192 KB
 
-__global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g) {
+__global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid_constant__ CUtensorMap tmHhi,
+                                                        const __grid_constant__ CUtensorMap tmHlo, const __grid_constant__ CUtensorMap tmW1hi,
+                                                        const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmW2hi,
+                                                        const __grid_constant__ CUtensorMap tmW2lo) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
@@ -366,8 +364,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a1_full, NUM_PROD); mbar_init(&a1_empty, 1);
+        for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a1_full, 1); mbar_init(&a1_empty, 1);
         mbar_init(&a2_full, G_EPI); mbar_init(&a2_empty, 1);
         for (int a = 0; a < 2; a++) {
             mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], G_EPI);
@@ -383,62 +381,36 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g) {
     const uint32_t tmem_base = tmem_base_s;
     // TMEM columns: accF[0] 0..127, accF[1] 128..255, accO[0] 256..383, accO[1] 384..511
 
-    if (warp >= G_PROD_WARP0 && warp < G_MMA_WARP) {
-        // =============================== producers ===============================
-        const int p = tid - G_PROD_WARP0 * 32;
-        uint32_t it_stage = 0, n_done = 0;
-        int pending = -1;
-        bool a1_pending = false;
-        for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
-            const size_t m0 = (size_t)tile * BM;
-            // ---- H tile (resident for the whole tile): 2 k-blocks x (hi, lo)
-            mbar_wait(&a1_empty, (n_done & 1) ^ 1);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int idx = i * 128 + p;                 // 2048 (row, chunk16) items of the [128 x 128] tile
-                const int r = idx >> 4, c16 = idx & 15, kb = c16 >> 3, c = c16 & 7;
-                const uint32_t off = (uint32_t)kb * (2 * BM * 128) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                const size_t ga = (m0 + r) * (size_t)BN + c16 * 8;
-                cp_async16(smem_u32(sA1) + off, g.Hhi + ga);
-                cp_async16(smem_u32(sA1) + BM * 128 + off, g.Hlo + ga);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            a1_pending = true;
-            // ---- the 16 weight k-block tiles of this tile, in MMA issue order
-            for (int st = 0; st < 8; st++) {
-                int is2, c;
-                ffn_step(st, is2, c);
-                for (int kb = 0; kb < 2; kb++, it_stage++) {
-                    const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
-                    const __nv_bfloat16* whi = is2 ? g.W2hi : g.W1hi;
-                    const __nv_bfloat16* wlo = is2 ? g.W2lo : g.W1lo;
-                    // F1(c): rows = hidden units c*128.., K = C;   F2(c): rows = outputs, K-columns = hidden units c*128..
-                    const size_t ld = is2 ? (size_t)g.F : (size_t)BN;
-                    const size_t row0 = is2 ? 0 : (size_t)c * 128, col0 = (is2 ? (size_t)c * 128 : 0) + (size_t)kb * BK;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int idx = i * 128 + p, r = idx >> 3, cc = idx & 7;
-                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
-                        const size_t gw = (row0 + r) * ld + col0 + cc * 8;
-                        cp_async16(sb + off, whi + gw);
-                        cp_async16(sb + BN * 128 + off, wlo + gw);
+    if (warp == G_PROD_WARP) {
+        // =============================== producer: one lane issues the TMA copies ===============================
+        if (lane == 0) {
+            uint32_t it_stage = 0, n_done = 0;
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                const int m0 = (int)(tile * BM);
+                // ---- H tile (resident for the whole tile): 2 k-blocks x (hi, lo)
+                mbar_wait(&a1_empty, (n_done & 1) ^ 1);
+                mbar_arrive_expect_tx(&a1_full, FFN_A_BYTES);
+                for (int kb = 0; kb < 2; kb++) {
+                    tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128), &tmHhi, &a1_full, kb * BK, m0);
+                    tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128) + BM * 128, &tmHlo, &a1_full, kb * BK, m0);
+                }
+                // ---- the 16 weight k-block tiles of this tile, in MMA issue order
+                for (int st = 0; st < 8; st++) {
+                    int is2, c;
+                    ffn_step(st, is2, c);
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
+                        mbar_arrive_expect_tx(&full_bar[s], FFN_RING_BYTES);
+                        // F1(c): rows = hidden units c*128.., K = C;   F2(c): rows = outputs, K-columns = hidden units c*128..
+                        const int crow = is2 ? 0 : c * 128, ccol = (is2 ? c * 128 : 0) + kb * BK;
+                        tma_load_2d(sb, is2 ? &tmW2hi : &tmW1hi, &full_bar[s], ccol, crow);
+                        tma_load_2d(sb + BN * 128, is2 ? &tmW2lo : &tmW1lo, &full_bar[s], ccol, crow);
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    // publish everything older than the group just committed
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (a1_pending) { mbar_arrive(&a1_full); a1_pending = false; }
-                    if (pending >= 0) mbar_arrive(&full_bar[pending]);
-                    pending = (int)s;
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (a1_pending) mbar_arrive(&a1_full);
-        if (pending >= 0) mbar_arrive(&full_bar[pending]);
     } else if (warp == G_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
@@ -589,19 +561,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g) {
     if (warp == G_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
-}
-
-cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    const size_t smem = (size_t)2 * FFN_A_BYTES + (size_t)FFN_STAGES * FFN_RING_BYTES + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    if (a.m_tiles == 0) return cudaSuccess;
-    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -824,6 +783,31 @@ cudaError_t split_weights(const float* w, size_t n, void** hi, void** lo) {
     return cudaGetLastError();
 }
 
+// ---- host: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point; no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 2-D bf16 tensor [rows][cols] with row stride `ld` elements; box = 128 rows x 64 columns (one SWIZZLE_128B k-block tile)
+static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstr[1] = {ld * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // M % 128 == 0, N % 128 == 0, K % 64 == 0
 cudaError_t gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
@@ -835,8 +819,31 @@ cudaError_t gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
     }
     const uint32_t items = a.m_tiles * a.n_chunks;
     if (items == 0) return cudaSuccess;
+    CUtensorMap tAh, tAl, tWh, tWl;
+    const uint64_t M = (uint64_t)a.m_tiles * BM, N = (uint64_t)a.n_chunks * BN;
+    if (!make_tmap(&tAh, a.Ahi, M, a.K, a.lda) || !make_tmap(&tAl, a.Alo, M, a.K, a.lda) || !make_tmap(&tWh, a.Whi, N, a.K, a.K) ||
+        !make_tmap(&tWl, a.Wlo, N, a.K, a.K))
+        return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)std::min<uint32_t>(items, (uint32_t)num_sms);
-    k_gemm_ws<<<grid, G_THREADS, smem, st>>>(a);
+    k_gemm_ws<<<grid, G_THREADS, smem, st>>>(a, tAh, tAl, tWh, tWl);
+    return cudaGetLastError();
+}
+
+cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)2 * FFN_A_BYTES + (size_t)FFN_STAGES * FFN_RING_BYTES + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.m_tiles == 0) return cudaSuccess;
+    CUtensorMap tHh, tHl, t1h, t1l, t2h, t2l;
+    const uint64_t T = (uint64_t)a.m_tiles * BM;
+    if (!make_tmap(&tHh, a.Hhi, T, BN, BN) || !make_tmap(&tHl, a.Hlo, T, BN, BN) || !make_tmap(&t1h, a.W1hi, a.F, BN, BN) ||
+        !make_tmap(&t1l, a.W1lo, a.F, BN, BN) || !make_tmap(&t2h, a.W2hi, BN, a.F, a.F) || !make_tmap(&t2l, a.W2lo, BN, a.F, a.F))
+        return cudaErrorInvalidValue;
+    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l);
     return cudaGetLastError();
 }
 
