@@ -180,6 +180,7 @@ template <int DH>
 __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, __nv_bfloat16* __restrict__ Ohi,
                                                    __nv_bfloat16* __restrict__ Olo, uint32_t npos, int C, int H) {
     __shared__ __align__(16) float sK[4][32][DH + 4], sV[4][32][DH + 4];
+    __shared__ __align__(16) uint32_t s_out[4][32 * (DH / 2)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * 4 + warp;
     if (item >= npos * (uint32_t)H) return;
@@ -229,14 +230,30 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV
         }
     }
     const float inv = (lane < R_COLS) ? 1.f / l : 0.f;  // the pad token row is written as zeros
-    const size_t ob = ((size_t)n * TOK_PER_POS + lane) * C + h * DH;
+    // split bf16 output.  A lane owns a token row (DH values = DH*2 bytes of hi and of lo); rows are transposed through a
+    // per-warp buffer so that each global store instruction covers whole 64-byte row segments instead of 32 scattered pieces.
+    uint32_t* stg = s_out[warp];
+    constexpr int WPR = DH / 2;  // packed words per row and array
+    uint32_t hiw[WPR], low[WPR];
 #pragma unroll
-    for (int d = 0; d < DH; d += 4) {
-        const float y[4] = {o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv};
-        uint2 hi, lo;
-        split4(y, hi, lo);
-        *(uint2*)(Ohi + ob + d) = hi;
-        *(uint2*)(Olo + ob + d) = lo;
+    for (int d = 0; d < DH; d += 2) split2f(o[d] * inv, o[d + 1] * inv, hiw[d >> 1], low[d >> 1]);
+    const size_t ob = (size_t)n * TOK_PER_POS * C + h * DH;  // row 0 of this position, this head's columns
+#pragma unroll
+    for (int arr = 0; arr < 2; arr++) {
+        const uint32_t* w = arr ? low : hiw;
+        __nv_bfloat16* gb = (arr ? Olo : Ohi) + ob;
+#pragma unroll
+        for (int cq = 0; cq < WPR / 4; cq++)
+            *(uint4*)(stg + lane * WPR + ((cq ^ ((lane >> 1) & (WPR / 4 - 1))) << 2)) = make_uint4(w[cq * 4], w[cq * 4 + 1], w[cq * 4 + 2], w[cq * 4 + 3]);
+        __syncwarp();
+        constexpr int LPR = WPR / 4;        // lanes per row (16-byte chunks per row)
+        constexpr int RPI = 32 / LPR;       // rows per instruction
+#pragma unroll
+        for (int jj = 0; jj < 32 / RPI; jj++) {
+            const int rr = jj * RPI + lane / LPR, cq = lane % LPR;
+            *(uint4*)(gb + (size_t)rr * C + cq * 8) = *(const uint4*)(stg + rr * WPR + ((cq ^ ((rr >> 1) & (LPR - 1))) << 2));
+        }
+        __syncwarp();
     }
 }
 

@@ -124,6 +124,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// ---- row-owner <-> coalesced transposes through a per-warp shared-memory buffer ---------------------------------------
+// In the epilogues a thread owns one row (its TMEM lane).  Touching global memory directly from that layout issues
+// warp instructions that hit 32 different rows with 16 bytes each (32 partial sectors): measured 2x slower kernels.
+// These helpers move 16 fp32 (or 16 bf16) columns of the warp's 32 rows through a swizzled [32][64 B] buffer so that
+// every global instruction covers whole 64-byte (fp32) / 32-byte (bf16) row segments.
+__device__ __forceinline__ void warp_store_f32x16(float* stg, int lane, float* gbase, size_t ld, const float* v) {
+#pragma unroll
+    for (int cq = 0; cq < 4; cq++)
+        *(float4*)(stg + lane * 16 + ((cq ^ ((lane >> 1) & 3)) << 2)) = make_float4(v[cq * 4], v[cq * 4 + 1], v[cq * 4 + 2], v[cq * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
+        *(float4*)(gbase + (size_t)rr * ld + cq * 4) = *(const float4*)(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_load_f32x16(float* stg, int lane, const float* gbase, size_t ld, float* v) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
+        *(float4*)(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2)) = *(const float4*)(gbase + (size_t)rr * ld + cq * 4);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int cq = 0; cq < 4; cq++) {
+        const float4 t = *(const float4*)(stg + lane * 16 + ((cq ^ ((lane >> 1) & 3)) << 2));
+        v[cq * 4] = t.x; v[cq * 4 + 1] = t.y; v[cq * 4 + 2] = t.z; v[cq * 4 + 3] = t.w;
+    }
+    __syncwarp();
+}
+// 16 bf16 columns (8 packed words per row) of the warp's 32 rows; buffer viewed as [32 rows][8 words]
+__device__ __forceinline__ void warp_store_bf16x16(uint32_t* stg, int lane, __nv_bfloat16* gbase, size_t ld, const uint32_t* w) {
+    *(uint4*)(stg + lane * 8 + (((lane >> 2) & 1) << 2)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *(uint4*)(stg + lane * 8 + ((((lane >> 2) & 1) ^ 1) << 2)) = make_uint4(w[4], w[5], w[6], w[7]);
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++) {
+        const int rr = jj * 16 + (lane >> 1), cq = lane & 1;
+        *(uint4*)(gbase + (size_t)rr * ld + cq * 8) = *(const uint4*)(stg + rr * 8 + ((cq ^ ((rr >> 2) & 1)) << 2));
+    }
+    __syncwarp();
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __grid_constant__ CUtensorMap tmAhi,
@@ -138,6 +183,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
     // kernel is almost entirely carved out for the operand ring, so repeated global reads would pay L2 latency)
     __shared__ __align__(16) float s_bias[2][BN], s_lng[BN], s_lnb[BN];
     __shared__ float s_red[2][2][BM];  // [item parity][column half][row]: LayerNorm partial sums
+    // per-warp transpose buffers [32 rows][16 floats]: a thread owns a row of the accumulator, but global stores are issued
+    // with lanes covering whole 64-byte row segments (sector-complete, 8 rows per instruction) instead of 32 scattered 16-byte pieces
+    __shared__ __align__(16) float s_stage[8][32 * 16];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == G_MMA_WARP) {
@@ -225,18 +273,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
                 // residual add + fp32 store of this thread's half row, then LayerNorm of the whole row with the
                 // partial sums exchanged with the thread that owns the other half
                 float x[64];
-                float* xrow = g.out + row * g.ldc + ch;
+                float* stg = s_stage[warp];
+                float* xblk = g.out + ((size_t)m0 + wq * 32) * g.ldc + ch;  // this warp's [32 rows][64 cols] block of X
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = *(const float4*)(sb + c0 + j);
-                        const float4 rr = *(const float4*)(xrow + c0 + j);
-                        x[c0 + j] = __uint_as_float(v[j]) + bv.x + rr.x; x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bv.y + rr.y;
-                        x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bv.z + rr.z; x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bv.w + rr.w;
-                        *(float4*)(xrow + c0 + j) = make_float4(x[c0 + j], x[c0 + j + 1], x[c0 + j + 2], x[c0 + j + 3]);
+                    for (int h = 0; h < 2; h++) {
+                        float rv[16];
+                        warp_load_f32x16(stg, lane, xblk + c0 + h * 16, g.ldc, rv);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) x[c0 + h * 16 + j] = __uint_as_float(v[h * 16 + j]) + sb[c0 + h * 16 + j] + rv[j];
+                        warp_store_f32x16(stg, lane, xblk + c0 + h * 16, g.ldc, x + c0 + h * 16);
                     }
                 }
                 // TMEM is drained: let the MMA warp start the next item while this thread normalises
@@ -255,19 +304,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
                 s_red[acc][eh][r] = var;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 const float rstd = rsqrtf((s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN) + 1e-5f);
-                uint4* ph = (uint4*)(g.out_hi + row * g.ldo + ch);
-                uint4* pl = (uint4*)(g.out_lo + row * g.ldo + ch);
+                __nv_bfloat16* hblk = g.out_hi + ((size_t)m0 + wq * 32) * g.ldo + ch;
+                __nv_bfloat16* lblk = g.out_lo + ((size_t)m0 + wq * 32) * g.ldo + ch;
 #pragma unroll
-                for (int j = 0; j < 64; j += 8) {
-                    uint32_t hi[4], lo[4];
+                for (int j = 0; j < 64; j += 16) {
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
+                    for (int e = 0; e < 16; e += 2) {
                         const float a = (x[j + e] - mean) * rstd * s_lng[ch + j + e] + s_lnb[ch + j + e];
                         const float b = (x[j + e + 1] - mean) * rstd * s_lng[ch + j + e + 1] + s_lnb[ch + j + e + 1];
                         split2(a, b, hi[e >> 1], lo[e >> 1]);
                     }
-                    ph[j >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    pl[j >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    warp_store_bf16x16((uint32_t*)stg, lane, hblk + j, g.ldo, hi);
+                    warp_store_bf16x16((uint32_t*)stg, lane, lblk + j, g.ldo, lo);
                 }
                 continue;
             }
@@ -295,20 +344,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
                         pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                 } else {
-                    float* out = g.out + row * g.ldc + col;
+                    float* stg = s_stage[warp];
+                    float* gbase = g.out + ((size_t)m0 + wq * 32) * g.ldc + col;  // row 0 of this warp's 32-row block
                     if (g.mode == GEMM_OUT_F32_RES) {
-                        const float* res = g.res + row * g.ldc + col;
+                        const float* rbase = g.res + ((size_t)m0 + wq * 32) * g.ldc + col;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 rr = *(const float4*)(res + j);
-                            o[j] += rr.x; o[j + 1] += rr.y; o[j + 2] += rr.z; o[j + 3] += rr.w;
+                        for (int h = 0; h < 2; h++) {
+                            float rv[16];
+                            warp_load_f32x16(stg, lane, rbase + h * 16, g.ldc, rv);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) o[h * 16 + j] += rv[j];
                         }
                     } else if (g.mode == GEMM_OUT_F32_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *(float4*)(out + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    warp_store_f32x16(stg, lane, gbase, g.ldc, o);
+                    warp_store_f32x16(stg, lane, gbase + 16, g.ldc, o + 16);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -357,6 +409,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN];
     __shared__ float s_red[2][2][BM];  // [tile parity][column half][row]: LayerNorm partial sums
+    __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == G_MMA_WARP) {
@@ -511,18 +564,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ch + ((uint32_t)(wq * 32) << 16);
             float x[64];
-            float* xrow = g.X + row * BN + ch;
+            float* stg = s_stage[warp];
+            float* xblk = g.X + ((size_t)tile * BM + wq * 32) * BN + ch;  // this warp's [32 rows][64 cols] block of X
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 bv = *(const float4*)(s_b2 + ch + c0 + jj);
-                    const float4 rr = *(const float4*)(xrow + c0 + jj);
-                    x[c0 + jj] = __uint_as_float(v[jj]) + bv.x + rr.x; x[c0 + jj + 1] = __uint_as_float(v[jj + 1]) + bv.y + rr.y;
-                    x[c0 + jj + 2] = __uint_as_float(v[jj + 2]) + bv.z + rr.z; x[c0 + jj + 3] = __uint_as_float(v[jj + 3]) + bv.w + rr.w;
-                    *(float4*)(xrow + c0 + jj) = make_float4(x[c0 + jj], x[c0 + jj + 1], x[c0 + jj + 2], x[c0 + jj + 3]);
+                for (int h = 0; h < 2; h++) {
+                    float rv[16];
+                    warp_load_f32x16(stg, lane, xblk + c0 + h * 16, BN, rv);
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj++)
+                        x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_b2[ch + c0 + h * 16 + jj] + rv[jj];
+                    warp_store_f32x16(stg, lane, xblk + c0 + h * 16, BN, x + c0 + h * 16);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -540,19 +595,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             s_red[oacc][eh][r] = var;
             asm volatile("bar.sync 2, 256;" ::: "memory");
             const float rstd = rsqrtf((s_red[oacc][0][r] + s_red[oacc][1][r]) * (1.f / BN) + 1e-5f);
-            uint4* ph = (uint4*)(g.out_hi + row * BN + ch);
-            uint4* pl = (uint4*)(g.out_lo + row * BN + ch);
+            __nv_bfloat16* hblk = g.out_hi + ((size_t)tile * BM + wq * 32) * BN + ch;
+            __nv_bfloat16* lblk = g.out_lo + ((size_t)tile * BM + wq * 32) * BN + ch;
 #pragma unroll
-            for (int jj = 0; jj < 64; jj += 8) {
-                uint32_t hi[4], lo[4];
+            for (int jj = 0; jj < 64; jj += 16) {
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
+                for (int e = 0; e < 16; e += 2) {
                     const float a = (x[jj + e] - mean) * rstd * s_lng[ch + jj + e] + s_lnb[ch + jj + e];
                     const float b = (x[jj + e + 1] - mean) * rstd * s_lng[ch + jj + e + 1] + s_lnb[ch + jj + e + 1];
                     split2(a, b, hi[e >> 1], lo[e >> 1]);
                 }
-                ph[jj >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                pl[jj >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                warp_store_bf16x16((uint32_t*)stg, lane, hblk + jj, BN, hi);
+                warp_store_bf16x16((uint32_t*)stg, lane, lblk + jj, BN, lo);
             }
         }
     }
@@ -582,6 +637,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
     uint8_t* qbuf = tokbuf + 2 * 4 * STEM_MAXK * 32;             // same shape, raw quality bytes
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_stage[4][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 8) {
@@ -723,21 +779,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const size_t row = (size_t)item * BM + warp * 32 + lane;  // token row: position = item*4 + warp, read = lane
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
-            float* out = g.X + row * BN;
+            float* oblk = g.X + ((size_t)item * BM + warp * 32) * BN;  // this warp's 32 token rows
             const float* rp = g.read_pos + (size_t)(lane < R_COLS ? lane : 0) * BN;
+            (void)row;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 bv = *(const float4*)(g.bias + c0 + j);
                     const float4 pv = *(const float4*)(rp + c0 + j);
-                    float4 o = make_float4(fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x, fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y,
-                                           fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z, fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w);
-                    if (lane >= R_COLS) o = make_float4(0.f, 0.f, 0.f, 0.f);  // the pad token of every position
-                    *(float4*)(out + c0 + j) = o;
+                    o[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x; o[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y;
+                    o[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z; o[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w;
                 }
+                if (lane >= R_COLS) {  // the pad token of every position
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = 0.f;
+                }
+                warp_store_f32x16(s_stage[warp], lane, oblk + c0, BN, o);
+                warp_store_f32x16(s_stage[warp], lane, oblk + c0 + 16, BN, o + 16);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
