@@ -195,10 +195,32 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV
     }
     float q[DH], o[DH];
 #pragma unroll
-    for (int d = 0; d < DH; d += 4) {
-        const float4 v = *(const float4*)(base + (size_t)lane * 3 * C + h * DH + d);
-        q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
-        o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+    for (int d = 0; d < DH; d++) o[d] = 0.f;
+    if constexpr (DH == 32) {
+        // the lane's own query row, loaded with whole 64-byte row segments per instruction and transposed through s_out
+        float* stq = (float*)s_out[warp];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
+                *(float4*)(stq + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2)) =
+                    *(const float4*)(base + (size_t)rr * 3 * C + h * DH + half * 16 + cq * 4);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int cq = 0; cq < 4; cq++) {
+                const float4 v = *(const float4*)(stq + lane * 16 + ((cq ^ ((lane >> 1) & 3)) << 2));
+                q[half * 16 + cq * 4] = v.x; q[half * 16 + cq * 4 + 1] = v.y; q[half * 16 + cq * 4 + 2] = v.z; q[half * 16 + cq * 4 + 3] = v.w;
+            }
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+            const float4 v = *(const float4*)(base + (size_t)lane * 3 * C + h * DH + d);
+            q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
+        }
     }
     __syncwarp();
     // two passes: all 31 scores first (registers), then softmax weights and the weighted sum of V.  exp via ex2.approx
