@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--e2e-launch-targets", type=int, default=0, help="targets per launch in the e2e region (default launch_targets/2)")
     ap.add_argument("--feature-threads", type=int, default=4, help="reference -t: host threads submitting targets")
     return ap.parse_args()
 
@@ -212,7 +213,7 @@ def main():
     n_steps = args.warmup + args.steps
     lt = min(args.launch_targets, max(1, rs.n // n_steps))
     nthr = max(1, min(args.feature_threads, threads))
-    lt_thread = max(32, lt // nthr)   # every feature thread stages its own launches (herro_b200/csrc/ctx.cu)
+    lt_thread = args.e2e_launch_targets or max(32, lt // 2)   # every feature thread stages its own launches (herro_b200/csrc/ctx.cu)
     ctx = Context(model, local_rank, args.window, args.batch_size, launch_targets=lt_thread)
     t0 = time.time()
     ctx.upload_reads(rs.seqs, rs.quals, rs.off)

@@ -89,7 +89,7 @@ struct PinVec {
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
     bool reserve(size_t want) {
         if (want <= cap) return true;
-        size_t ncap = (n == 0 && cap == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
+        size_t ncap = (n == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
         T* np = nullptr;
         int cur = -1;
         if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) cudaSetDevice(dev);  // growth is rare: only then touch the runtime
@@ -680,9 +680,14 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
 // Back-pressure: at most 2 batches wait in the queue.
 void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) {
     if (b.tgt.empty()) return;
-    size_t* h = ctx->cap_hint;
-    h[0] = std::max(h[0], b.tgt.size()); h[1] = std::max(h[1], b.win.size()); h[2] = std::max(h[2], b.ovl.size());
-    h[3] = std::max(h[3], b.ow.size()); h[4] = std::max(h[4], b.cig.size());
+    // capacity hint for fresh staging batches: what a full launch_targets-sized batch of this workload needs
+    // (per-target averages of this batch, scaled), so that pinned memory is allocated once and not grown step by step
+    {
+        size_t* h = ctx->cap_hint;
+        const double scale = std::max(1.0, (double)ctx->opt.launch_targets / (double)b.tgt.size()) * 1.25;
+        const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
+        for (int i = 0; i < 5; i++) h[i] = std::max(h[i], (size_t)((double)cur[i] * scale) + 64);
+    }
     ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });
     ctx->queue.push_back(std::move(b));
     b = HostBatch(ctx->device);
@@ -693,11 +698,11 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) 
 // (pinned allocations are slow and serialise with the worker's CUDA calls, so growth in small steps is avoided).
 void acquire_batch(hb_ctx* ctx, HostBatch& b) {
     std::unique_lock<std::mutex> lk(ctx->mu);
-    if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); return; }
     size_t h[5];
-    for (int i = 0; i < 5; i++) h[i] = ctx->cap_hint[i] + ctx->cap_hint[i] / 8;
+    for (int i = 0; i < 5; i++) h[i] = ctx->cap_hint[i];
+    if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
+    else b = HostBatch(ctx->device);
     lk.unlock();
-    b = HostBatch(ctx->device);
     if (h[0]) { b.tgt.reserve(h[0]); b.win.reserve(h[1]); b.ovl.reserve(h[2]); b.ow.reserve(h[3]); b.cig.reserve(h[4]); }
 }
 
