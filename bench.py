@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--e2e-launch-targets", type=int, default=0, help="targets per launch in the e2e region (default launch_targets/2)")
+    ap.add_argument("--e2e-launch-targets", type=int, default=0, help="launch_targets of the context in the e2e region (default: same as --launch-targets; the library divides it among the submitting threads)")
     ap.add_argument("--feature-threads", type=int, default=4, help="reference -t: host threads submitting targets")
     return ap.parse_args()
 
@@ -213,7 +213,7 @@ def main():
     n_steps = args.warmup + args.steps
     lt = min(args.launch_targets, max(1, rs.n // n_steps))
     nthr = max(1, min(args.feature_threads, threads))
-    lt_thread = args.e2e_launch_targets or max(32, lt // 2)   # every feature thread stages its own launches (herro_b200/csrc/ctx.cu)
+    lt_thread = args.e2e_launch_targets or lt   # shared by the feature threads: each stages lt / threads targets per launch (ctx.cu)
     ctx = Context(model, local_rank, args.window, args.batch_size, launch_targets=lt_thread)
     t0 = time.time()
     ctx.upload_reads(rs.seqs, rs.quals, rs.off)
@@ -315,7 +315,8 @@ def main():
                        "l2": "inputs larger than L2 (per-launch working set >> 126 MB)",
                        "host_feature_threads": nthr, "host_worker_busy_ms_per_launch": st["ms_worker_busy"] / max(st["device_launches"], 1),
                        "host_worker_gpu_wait_ms_per_launch": st["ms_worker_gpu_wait"] / max(st["device_launches"], 1),
-                       "launches_in_e2e_region": st["device_launches"], "harness_seconds": r_e2e["seconds"], "submit_seconds_sum": r_e2e["submit_seconds_sum"], "last_launch_targets": st["last_launch_targets"], "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
+                       "launches_in_e2e_region": st["device_launches"], "host_allocs_in_e2e_region": st["host_allocs"], "host_alloc_ms_in_e2e_region": st["ms_host_alloc"],
+                       "submit_backpressure_ms_sum": st["ms_submit_wait"], "worker_phase_ms_per_launch": [round(x / max(st["device_launches"], 1), 3) for x in st["ms_worker_phase"][:7]], "harness_seconds": r_e2e["seconds"], "submit_seconds_sum": r_e2e["submit_seconds_sum"], "last_launch_targets": st["last_launch_targets"], "host_windowing_s": t_windowing, "read_store_upload_s": t_upload, "generate_s": t_gen,
                        "model": {"channels": cfg.channels, "heads": cfg.heads, "layers": cfg.layers, "ffn": cfg.ffn,
                                  "stem_k": cfg.stem_k, "collapse": cfg.collapse, "weights": "random init (no checkpoint offline)"}},
             "e2e": {"value": bases_e2e_all / t_e2e, "unit": UNIT,

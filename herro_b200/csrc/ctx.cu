@@ -34,17 +34,39 @@ thread_local std::string g_create_err;
 thread_local std::string* t_err_sink = nullptr;
 std::atomic<uint64_t> g_ctx_generation{1};  // the launch worker reports into its own string
 
+// allocation accounting (hb_stats.host_allocs / ms_host_alloc): page-locked and device allocations are slow and
+// serialise with every other CUDA call of the process, so the steady state must not make any
+std::atomic<uint64_t> g_allocs{0}, g_alloc_ns{0}, g_submit_wait_ns{0};
+struct AllocScope {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~AllocScope() {
+        g_allocs.fetch_add(1, std::memory_order_relaxed);
+        g_alloc_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                             std::memory_order_relaxed);
+    }
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t st = nullptr;  // lane buffers: grown in stream order from the device's memory pool, because
+                                // cudaMalloc/cudaFree synchronise the whole device and would stall the other lanes
     cudaError_t ensure(size_t bytes, bool keep = false) {
         if (bytes <= cap) return cudaSuccess;
-        size_t ncap = bytes + bytes / 4 + 256;
+        AllocScope as_;
+        size_t ncap = bytes + bytes / 2 + 256;
         void* np = nullptr;
-        cudaError_t e = cudaMalloc(&np, ncap);
-        if (e != cudaSuccess) return e;
-        if (keep && p && cap) cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice);
-        if (p) cudaFree(p);
+        if (st) {
+            cudaError_t e = cudaMallocAsync(&np, ncap, st);
+            if (e != cudaSuccess) return e;
+            if (keep && p && cap) cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+            if (p) cudaFreeAsync(p, st);
+        } else {
+            cudaError_t e = cudaMalloc(&np, ncap);
+            if (e != cudaSuccess) return e;
+            if (keep && p && cap) cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice);
+            if (p) cudaFree(p);
+        }
         p = np;
         cap = ncap;
         return cudaSuccess;
@@ -58,10 +80,11 @@ struct PinBuf {
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        AllocScope as_;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        size_t ncap = bytes + bytes / 4 + 256;
+        size_t ncap = bytes + bytes / 2 + 256;
         cudaError_t e = cudaMallocHost(&p, ncap);
         if (e == cudaSuccess) cap = ncap;
         return e;
@@ -89,6 +112,7 @@ struct PinVec {
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
     bool reserve(size_t want) {
         if (want <= cap) return true;
+        AllocScope as_;
         size_t ncap = (n == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
         T* np = nullptr;
         int cur = -1;
@@ -183,6 +207,14 @@ struct hb_ctx {
         uint64_t rows_cap = 0;
         LastLaunch last;
         std::thread worker;
+        void bind_stream() {
+            DevBuf* bufs[] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
+                              &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
+                              &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
+                              &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
+                              &d_counters, &d_ws, &d_logits, &d_info};
+            for (DevBuf* b : bufs) b->st = stream;
+        }
         void release() {
             DevBuf* bufs[] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
                               &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
@@ -196,13 +228,13 @@ struct hb_ctx {
             if (stream) cudaStreamDestroy(stream);
         }
     };
-    static constexpr int NUM_LANES = 2;
-    Lane lanes[NUM_LANES];
+    static constexpr int MAX_LANES = 4;
+    Lane lanes[MAX_LANES];
+    int n_lanes = 3;     // HERRO_B200_LANES overrides (1..4)
     int last_lane = -1;  // lane of the most recently finished launch (debug taps / replay)
-    uint32_t chunk_pos = 8192;
+    uint32_t chunk_pos = 65536;  // supported positions per forward pass (HERRO_B200_CHUNK_POS): one pass per launch unless huge
 
     std::deque<Result> results;
-    std::unordered_map<uint8_t*, void*> live;  // seqs pointer -> malloc block
     hb_stats stats{};
 
     // launch worker: batches are processed asynchronously so that the host can stage batch i+1
@@ -216,6 +248,8 @@ struct hb_ctx {
     std::string worker_err;
     bool idle() const { return queue.empty() && busy == 0; }
     size_t cap_hint[5] = {0, 0, 0, 0, 0};  // largest batch array sizes seen (tgt, win, ovl, ow, cig)
+    std::atomic<uint32_t> n_slots{0};       // submitting threads registered since the last flush
+    uint64_t alloc_base[3] = {0, 0, 0};     // g_allocs / g_alloc_ns / g_submit_wait_ns at the last hb_reset_stats
     uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
 };
 
@@ -502,9 +536,10 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     if (hbt.tgt.empty()) return HB_OK;
     const double t_begin = now_ms();
-    double t_wait = 0;
-#define SYNC_TIMED() do { const double t__ = now_ms(); CK(cudaStreamSynchronize(L->stream)); t_wait += now_ms() - t__; } while (0)
+    double t_wait = 0, t_mark = t_begin;
     hb_stats S{};  // merged into ctx->stats under the lock at the end
+#define SYNC_TIMED() do { const double t__ = now_ms(); CK(cudaStreamSynchronize(L->stream)); t_wait += now_ms() - t__; } while (0)
+#define PHASE(i) do { const double t__ = now_ms(); S.ms_worker_phase[i] += t__ - t_mark; t_mark = t__; } while (0)
     std::vector<Result> out_results;
     const uint32_t W = ctx->opt.window_size;
     int rc = ensure_batch_buffers(ctx, L, hbt);
@@ -524,6 +559,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     uint64_t launches = 0;
     BatchView b;
     uint64_t total_rows = 0;
+    PHASE(0);
     L->kt.on = true;
     L->kt.st = L->stream;
     for (int attempt = 0;; attempt++) {
@@ -538,7 +574,9 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         CK(cudaEventRecord(L->ev[2], L->stream));
         launches += launch_features_c1(b, L->stream, L->kt);  // ref_lmax + scan; the work list needs its buffers first
         CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, L->stream));
+        PHASE(1);
         SYNC_TIMED();
+        PHASE(2);
         total_rows = (uint64_t)h_cnt[CNT_TOTAL_ROWS] | ((uint64_t)h_cnt[CNT_TOTAL_ROWS + 1] << 32);
         if (!h_cnt[CNT_OVERFLOW]) break;
         if (attempt >= 2) return fail(ctx, HB_ERR_CAPACITY, "row arena overflow persisted after regrowth");
@@ -550,7 +588,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     CK(L->d_fwd_row.ensure(std::max<uint64_t>(n_sup, 1) * 4));
     CK(L->d_logits.ensure(std::max<uint64_t>(n_sup, 1) * 5 * 4));
     CK(L->d_info.ensure(std::max<uint64_t>(n_sup, 1) * 4));
-    CK(L->d_ws.ensure(fwd_workspace_bytes(ctx->wt, ctx->chunk_pos)));
+    CK(L->d_ws.ensure(fwd_workspace_bytes(ctx->wt, (uint32_t)std::min<uint64_t>(ctx->chunk_pos, std::max<uint64_t>(n_sup, 1)))));
     b = make_view(ctx, L, hbt);
     CK(cudaEventRecord(L->ev[3], L->stream));
     rc = launch_tail(ctx, L, b, n_sup, &launches);
@@ -570,12 +608,16 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     CK(cudaMemcpyAsync(h_nsup, b.w_nsup, nw * 4, cudaMemcpyDeviceToHost, L->stream));
     CK(cudaMemcpyAsync(h_terr, b.tgt_err, nt * 4, cudaMemcpyDeviceToHost, L->stream));
     CK(cudaMemcpyAsync(h_sel, b.sel_ow, nw * TOP_K * 4, cudaMemcpyDeviceToHost, L->stream));
+    // the emitted bytes of all windows are contiguous from offset 0 and number at most one per matrix row, so the
+    // row count (known since the first wait) bounds the copy: no second round trip for the exact size
+    CK(L->pin_out.ensure(total_rows + 16));
+    if (total_rows) CK(cudaMemcpyAsync(L->pin_out.p, b.out_bytes, total_rows, cudaMemcpyDeviceToHost, L->stream));
+    PHASE(3);
     SYNC_TIMED();
+    PHASE(4);
     const uint64_t total_out = (uint64_t)h_cnt[CNT_TOTAL_OUT] | ((uint64_t)h_cnt[CNT_TOTAL_OUT + 1] << 32);
-    CK(L->pin_out.ensure(total_out + 16));
-    if (total_out) CK(cudaMemcpyAsync(L->pin_out.p, b.out_bytes, total_out, cudaMemcpyDeviceToHost, L->stream));
-    SYNC_TIMED();
-    S.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_out;
+    if (total_out > total_rows) return fail(ctx, HB_ERR_CAPACITY, "consensus emitted more bytes than matrix rows");
+    S.d2h_bytes += CNT_N * 4 + nw * 16 + nt * 4 + nw * TOP_K * 4 + total_rows;
 
     // ---- timing
     float ms;
@@ -628,6 +670,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         corrected += r.seq.size();
         out_results.push_back(std::move(r));
     }
+    PHASE(5);
     S.targets += nt;
     S.windows += nw;
     S.overlap_windows += hbt.ow.size();
@@ -669,6 +712,8 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         T.pileup_algo_bytes += S.pileup_algo_bytes; T.gemm_flops += S.gemm_flops; T.forward_flops += S.forward_flops;
         T.ms_features += S.ms_features; T.ms_forward += S.ms_forward; T.ms_consensus += S.ms_consensus;
         for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) { T.ms_kernel[i] += S.ms_kernel[i]; T.n_kernel[i] += S.n_kernel[i]; }
+        S.ms_worker_phase[6] = now_ms() - t_mark;
+        for (int i = 0; i < 8; i++) T.ms_worker_phase[i] += S.ms_worker_phase[i];
         for (auto& r : out_results) ctx->results.push_back(std::move(r));
         L->last = std::move(ll);
         ctx->last_lane = (int)(L - ctx->lanes);
@@ -680,15 +725,21 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
 // Back-pressure: at most 2 batches wait in the queue.
 void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) {
     if (b.tgt.empty()) return;
-    // capacity hint for fresh staging batches: what a full launch_targets-sized batch of this workload needs
-    // (per-target averages of this batch, scaled), so that pinned memory is allocated once and not grown step by step
+    // capacity hint for staging batches: the largest arrays handed over so far plus a margin, so that pinned memory is
+    // allocated once per batch object and then recycled.  (No extrapolation from partial batches: a two-target
+    // remainder scaled to a full launch once produced hints several times too large, and every pooled batch was then
+    // re-pinned inside the next run.)
     {
         size_t* h = ctx->cap_hint;
-        const double scale = std::max(1.0, (double)ctx->opt.launch_targets / (double)b.tgt.size()) * 1.25;
         const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
-        for (int i = 0; i < 5; i++) h[i] = std::max(h[i], (size_t)((double)cur[i] * scale) + 64);
+        for (int i = 0; i < 5; i++)
+            if (cur[i] > h[i]) h[i] = cur[i] + cur[i] / 4 + 64;
     }
-    ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });
+    if (ctx->queue.size() >= 2) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->cv_idle.wait(lk, [&] { return ctx->queue.size() < 2; });
+        g_submit_wait_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+    }
     ctx->queue.push_back(std::move(b));
     b = HostBatch(ctx->device);
     ctx->cv_work.notify_one();
@@ -716,6 +767,7 @@ hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
     for (auto& sl : ctx->slots)
         if (sl->owner == me) { tl_ctx = ctx; tl_slot = sl.get(); tl_gen = ctx->generation; return tl_slot; }
     ctx->slots.emplace_back(new hb_ctx::ThreadSlot{me, HostBatch(ctx->device)});
+    ctx->n_slots.store((uint32_t)ctx->slots.size());
     tl_ctx = ctx; tl_slot = ctx->slots.back().get(); tl_gen = ctx->generation;
     return tl_slot;
 }
@@ -859,16 +911,26 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     }
     if (cuda_device < 0 || cuda_device >= ndev) { ctx->err = "cuda_device out of range"; return bail(HB_ERR_ARG); }
     if (cudaSetDevice(cuda_device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(HB_ERR_CUDA); }
-    for (auto& L : ctx->lanes) {
+    if (const char* e = getenv("HERRO_B200_CHUNK_POS")) ctx->chunk_pos = (uint32_t)std::min(std::max(atoi(e), 128), 65536);
+    if (const char* e = getenv("HERRO_B200_LANES")) ctx->n_lanes = std::min(std::max(atoi(e), 1), (int)hb_ctx::MAX_LANES);
+    for (int li = 0; li < ctx->n_lanes; li++) {
+        auto& L = ctx->lanes[li];
         if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(HB_ERR_CUDA); }
         for (auto& e : L.ev)
             if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(HB_ERR_CUDA); }
+        L.bind_stream();
+    }
+    {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        uint64_t keep = UINT64_MAX;
+        if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     if (features_configure(ctx->opt.window_size) != cudaSuccess) { ctx->err = "kernel attribute setup failed (not an sm_100a device?)"; return bail(HB_ERR_CUDA); }
     int rc = load_weights(ctx, model_path);
     if (rc) return bail(rc);
     ctx->generation = g_ctx_generation.fetch_add(1);
-    for (int i = 0; i < hb_ctx::NUM_LANES; i++) ctx->lanes[i].worker = std::thread(worker_main, ctx, i);
+    for (int i = 0; i < ctx->n_lanes; i++) ctx->lanes[i].worker = std::thread(worker_main, ctx, i);
     *out = ctx;
     return HB_OK;
 }
@@ -891,7 +953,6 @@ void hb_destroy(hb_ctx* ctx) {
     ctx->slots.clear();
     ctx->queue.clear();
     ctx->pool.clear();
-    for (auto& kv : ctx->live) free(kv.second);
     delete ctx;
 }
 
@@ -983,7 +1044,11 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
     const int rc = append_target(ctx, slot->batch, P, ovl, n_ovl);
     t_err_sink = nullptr;
     if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
-    if (slot->batch.tgt.size() >= ctx->opt.launch_targets) {
+    // `launch_targets` is shared by the submitting threads: each stages launch_targets / n_threads targets per launch,
+    // so the targets in flight (and the latency to the first launch) do not grow with the thread count
+    const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
+    const uint32_t thr = std::min(lt, std::max(32u, lt / ns));
+    if (slot->batch.tgt.size() >= thr) {
         std::unique_lock<std::mutex> lk(ctx->mu);
         enqueue_batch(ctx, lk, slot->batch);
     }
@@ -1030,6 +1095,7 @@ int hb_flush(hb_ctx* ctx) {
     std::unique_lock<std::mutex> lk(ctx->mu);
     for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch);  // must not race with hb_submit_* (see header)
     ctx->slots.clear();                                  // slots of finished feature threads are dropped;
+    ctx->n_slots.store(0);
     ctx->generation = g_ctx_generation.fetch_add(1);    // live threads re-register on their next submit
     ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
     const int rc = ctx->worker_rc;
@@ -1037,24 +1103,34 @@ int hb_flush(hb_ctx* ctx) {
     return rc;
 }
 
+// Result block handed to the caller: [seg_len: n_segs u32, padded to 16][tag: u64 distance back to the block start,
+// u64 magic][seq bytes].  hb_release_result finds the block from the tag in front of `seqs`, so neither call needs a
+// table (or the context lock while copying).
+static constexpr uint64_t RESULT_MAGIC = 0x4842524553303031ull;
+
 int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg_len, uint32_t* n_segs) {
     if (!ctx || !rid || !seqs || !seg_len || !n_segs) return HB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (ctx->results.empty()) return 0;
-    Result r = std::move(ctx->results.front());
-    ctx->results.pop_front();
+    Result r;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->results.empty()) return 0;
+        r = std::move(ctx->results.front());
+        ctx->results.pop_front();
+    }
     const size_t ns = r.seg_len.size();
-    const size_t hdr = (ns * 4 + 15) & ~(size_t)15;
+    const size_t hdr = ((ns * 4 + 15) & ~(size_t)15) + 16;
     uint8_t* blk = (uint8_t*)malloc(hdr + r.seq.size() + 16);
-    if (!blk) return fail(ctx, HB_ERR_CAPACITY, "out of host memory");
+    if (!blk) { std::lock_guard<std::mutex> lk(ctx->mu); return fail(ctx, HB_ERR_CAPACITY, "out of host memory"); }
     memcpy(blk, r.seg_len.data(), ns * 4);
+    const uint64_t tag[2] = {(uint64_t)hdr, RESULT_MAGIC};
+    memcpy(blk + hdr - 16, tag, 16);
     memcpy(blk + hdr, r.seq.data(), r.seq.size());
     *rid = r.rid;
     *seg_len = (uint32_t*)blk;
     *seqs = blk + hdr;
     *n_segs = (uint32_t)ns;
-    ctx->live[*seqs] = blk;
     if (r.status != HB_OK) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->err = "target " + std::to_string(r.rid) + ": input the reference would panic on (malformed CIGAR / window)";
         return r.status;
     }
@@ -1063,21 +1139,26 @@ int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg
 
 void hb_release_result(hb_ctx* ctx, uint8_t* seqs) {
     if (!ctx || !seqs) return;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    auto it = ctx->live.find(seqs);
-    if (it != ctx->live.end()) { free(it->second); ctx->live.erase(it); }
+    uint64_t tag[2];
+    memcpy(tag, seqs - 16, 16);
+    if (tag[1] != RESULT_MAGIC) return;  // not a block of hb_poll_corrected
+    free(seqs - tag[0]);
 }
 
 int hb_get_stats(hb_ctx* ctx, hb_stats* out) {
     if (!ctx || !out) return HB_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     *out = ctx->stats;
+    out->host_allocs = g_allocs.load() - ctx->alloc_base[0];
+    out->ms_host_alloc = (double)(g_alloc_ns.load() - ctx->alloc_base[1]) * 1e-6;
+    out->ms_submit_wait = (double)(g_submit_wait_ns.load() - ctx->alloc_base[2]) * 1e-6;
     return HB_OK;
 }
 int hb_reset_stats(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->stats = hb_stats{};
+    ctx->alloc_base[0] = g_allocs.load(); ctx->alloc_base[1] = g_alloc_ns.load(); ctx->alloc_base[2] = g_submit_wait_ns.load();
     return HB_OK;
 }
 

@@ -324,6 +324,10 @@ struct FwdWs {
     __nv_bfloat16 *Hhi, *Hlo, *Fhi, *Flo;
     size_t bytes;
 };
+static bool ffn_is_fused(const FwdWeights& wt) {
+    static const bool no_ln = getenv("HERRO_B200_NO_FUSE_LN") != nullptr, no_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;
+    return wt.C == 128 && wt.F == 512 && !no_ln && !no_ffn;
+}
 static FwdWs carve(const FwdWeights& wt, size_t npos, uint8_t* base) {
     const size_t np = (npos + 127) / 128 * 128;  // positions padded to a GEMM tile
     const size_t T = np * TOK_PER_POS;
@@ -334,8 +338,10 @@ static FwdWs carve(const FwdWeights& wt, size_t npos, uint8_t* base) {
     w.Z = (float*)(base + o); o += al256(np * wt.D * 4);
     w.Hhi = (__nv_bfloat16*)(base + o); o += al256(T * wt.C * 2);
     w.Hlo = (__nv_bfloat16*)(base + o); o += al256(T * wt.C * 2);
-    w.Fhi = (__nv_bfloat16*)(base + o); o += al256(T * wt.F * 2);
-    w.Flo = (__nv_bfloat16*)(base + o); o += al256(T * wt.F * 2);
+    // the [T,F] hidden activations exist in memory only on the unfused FFN path
+    const size_t TF = ffn_is_fused(wt) ? 0 : T;
+    w.Fhi = (__nv_bfloat16*)(base + o); o += al256(TF * wt.F * 2);
+    w.Flo = (__nv_bfloat16*)(base + o); o += al256(TF * wt.F * 2);
     w.bytes = o;
     return w;
 }
@@ -418,7 +424,6 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
     static const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid
     const bool fuse_ln = (C == 128) && !no_fuse;
-    static const bool no_fuse_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;  // debugging aid
     kt.begin(K_LAYERNORM);
     k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
     kt.end(); nl++;
@@ -441,7 +446,7 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
         }
         const float* ng = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_g : wt.lnf_g;
         const float* nb = (l + 1 < wt.layers) ? wt.layer[l + 1].ln1_b : wt.lnf_b;
-        if (fuse_ln && F == 512 && !no_fuse_ffn) {
+        if (ffn_is_fused(wt)) {
             // FFN1 -> ReLU -> FFN2 + residual + next LayerNorm in one kernel; the hidden activations stay on chip.
             // In-place on H is safe: the tile's H rows are only overwritten after all of its MMAs have completed.
             FfnArgs fa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_1.hi, (const __nv_bfloat16*)ly.s_1.lo,

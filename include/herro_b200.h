@@ -149,6 +149,12 @@ typedef struct hb_stats {
     uint64_t last_launch_targets, last_launch_windows, last_launch_bases; /* what hb_replay_last_launch re-runs */
     double ms_worker_busy;   /* host wall time the launch worker spent inside launches (staging+GPU+copy-back) */
     double ms_worker_gpu_wait; /* of which: blocked in stream synchronisation                               */
+    uint64_t host_allocs;    /* page-locked / device allocations made since the last reset (0 in steady state)  */
+    double ms_host_alloc;    /* wall time spent in them                                                         */
+    double ms_submit_wait;   /* wall time hb_submit_* callers were blocked on back-pressure (summed over threads) */
+    double ms_worker_phase[8]; /* launch-worker wall time by phase: 0 buffers+H2D enqueue, 1 feature launches,
+                                  2 wait (row counts), 3 forward+consensus launches, 4 wait (results),
+                                  5 per-read reassembly, 6 publish                                               */
 } hb_stats;
 int hb_get_stats(hb_ctx* ctx, hb_stats* out);
 int hb_reset_stats(hb_ctx* ctx);

@@ -86,3 +86,32 @@ def test_cli_fastq_oec_to_fasta(tmp_path):
             d = descs[rid].encode() if descs[rid] is not None else None
             want += fasta_records(rs.ids[rid].encode(), d, segs).split(b">")[1:]
     assert got == sorted(want) and len(got) > 0
+
+
+def test_forward_chunking_invariance(monkeypatch):
+    """The forward pass over the supported positions is split into passes of HERRO_B200_CHUNK_POS positions
+    (one pass per launch by default); the split must not change a single emitted base or logit."""
+    rs = helpers.small_readset(n_reads=40, mean_len=9000, seed=11)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    monkeypatch.setenv("HERRO_B200_CHUNK_POS", "200")   # not a multiple of the 128-position GEMM tile; ragged last pass
+    b = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    assert a["stats"]["supported"] > 3 * 200
+    assert b["stats"]["kernel_launches"] > a["stats"]["kernel_launches"]
+    assert a["segments"] == b["segments"]
+    for key, wa in a["windows"].items():
+        wb = b["windows"][key]
+        assert np.array_equal(wa["bases_logits"], wb["bases_logits"]), key
+        assert np.array_equal(wa["info_logits"], wb["info_logits"]), key
+
+
+def test_lane_count_invariance(monkeypatch):
+    """One launch lane or four: same records (HERRO_B200_LANES only changes how launches overlap)."""
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=12)
+    model = helpers.model_path(seed=3)
+    monkeypatch.setenv("HERRO_B200_LANES", "1")
+    a = helpers.run_product(rs, model, 4096, 64, launch_targets=4)
+    monkeypatch.setenv("HERRO_B200_LANES", "4")
+    b = helpers.run_product(rs, model, 4096, 64, launch_targets=4)
+    assert a["segments"] == b["segments"]
+    assert b["stats"]["device_launches"] >= 4
