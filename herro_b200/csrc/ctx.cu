@@ -381,6 +381,25 @@ int load_weights(hb_ctx* ctx, const char* path) {
             !split(ly.w1, (size_t)F * C, ly.s_1) || !split(ly.w2, (size_t)C * F, ly.s_2)) return HB_ERR_CUDA;
     }
     if (!split(wt.wc, (size_t)D * 31 * C, wt.s_c)) return HB_ERR_CUDA;
+    // head-grouped copy of Wqkv / bqkv for the fused QKV+attention kernel: row (h, s, d) = row s*C + h*32 + d (s = q,k,v)
+    if (C == 128 && wt.H == 4) {
+        for (int l = 0; l < wt.layers; l++) {
+            const std::string p = "l" + std::to_string(l) + ".";
+            const float *hw, *hbias;
+            if (!need(p + "wqkv", (size_t)3 * C * C, hw) || !need(p + "bqkv", 3 * (size_t)C, hbias)) return HB_ERR_MODEL;
+            std::vector<float> wp((size_t)3 * C * C), bp((size_t)3 * C);
+            for (int h = 0; h < 4; h++)
+                for (int sI = 0; sI < 3; sI++)
+                    for (int d = 0; d < 32; d++) {
+                        const size_t dst = (size_t)h * 96 + sI * 32 + d, src = (size_t)sI * C + h * 32 + d;
+                        memcpy(&wp[dst * C], hw + src * C, (size_t)C * 4);
+                        bp[dst] = hbias[src];
+                    }
+            const float* dwp = nullptr;
+            if (!upload(wp.data(), wp.size(), dwp) || !upload(bp.data(), bp.size(), wt.layer[l].bqkvp)) return HB_ERR_CUDA;
+            if (!split(dwp, wp.size(), wt.layer[l].s_qkvp)) return HB_ERR_CUDA;
+        }
+    }
     // W' of the tensor-core stem: [C][taps*16] = tab (11 token slots), wq twice (q_hi, q_lo columns), zero padding
     wt.stem_kblocks = 0;
     if (C == 128 && K <= 64 && !getenv("HERRO_B200_STEM_SIMT")) {

@@ -429,13 +429,21 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     kt.end(); nl++;
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
-        gemm(wt, GEMM_OUT_F32, ws.Hhi, ws.Hlo, C, ly.s_qkv, ly.bqkv, ws.QKV, nullptr, 3 * C, nullptr, nullptr, 0, T, 3 * C, C, st, kt); nl++;
-        // attention writes its (split) output over the LN buffers: the QKV contraction has consumed them (stream order)
-        const unsigned ab = (unsigned)(((size_t)np_pad * H + 3) / 4);
-        kt.begin(K_ATTENTION);
-        if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);
-        else k_attention<32><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);  // head_dim validated at load
-        kt.end(); nl++;
+        const bool no_fuse_attn = getenv("HERRO_B200_NO_FUSE_ATTN") != nullptr;  // debugging aid / A-B parity test
+        if (ly.bqkvp && !no_fuse_attn) {
+            // QKV projection + attention in one kernel (q, k, v stay on chip); output over the LN buffers, tile-local in-place
+            QkvAttnArgs qa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_qkvp.hi, (const __nv_bfloat16*)ly.s_qkvp.lo, ly.bqkvp, ws.Hhi, ws.Hlo,
+                           (uint32_t)(T / 128)};
+            kt.begin(K_ATTENTION); qkv_attn_tc(qa, wt.num_sms, st); kt.end(); nl++;
+        } else {
+            gemm(wt, GEMM_OUT_F32, ws.Hhi, ws.Hlo, C, ly.s_qkv, ly.bqkv, ws.QKV, nullptr, 3 * C, nullptr, nullptr, 0, T, 3 * C, C, st, kt); nl++;
+            // attention writes its (split) output over the LN buffers: the QKV contraction has consumed them (stream order)
+            const unsigned ab = (unsigned)(((size_t)np_pad * H + 3) / 4);
+            kt.begin(K_ATTENTION);
+            if (C / H == 16) k_attention<16><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);
+            else k_attention<32><<<ab, 128, 0, st>>>(ws.QKV, ws.Hhi, ws.Hlo, (uint32_t)np_pad, C, H);  // head_dim validated at load
+            kt.end(); nl++;
+        }
         // out-proj + residual (+ LN2 -> split H).  In-place on H is safe: a row's outputs are written by the
         // thread that owns the row only after every MMA that reads the tile has completed (tfull barrier).
         if (fuse_ln) {

@@ -18,6 +18,8 @@ struct SplitW {  // bf16 hi / lo split of an fp32 weight matrix [N,K] (gemm_tc.c
 struct FwdLayer {
     const float *ln1_g, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
     SplitW s_qkv, s_o, s_1, s_2;
+    SplitW s_qkvp;               // Wqkv with rows regrouped per head [H][q(32) | k(32) | v(32)][C] (fused QKV+attention kernel)
+    const float* bqkvp = nullptr;  // bqkv in the same order; nullptr: fused kernel unavailable
 };
 
 struct FwdWeights {
@@ -63,6 +65,14 @@ struct FfnArgs {  // k_ffn_ws: fused FFN for C == 128, F == 512
     uint32_t F, m_tiles;
 };
 cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st);
+struct QkvAttnArgs {  // k_qkv_attn_ws: QKV projection + read-axis attention for C == 128, 4 heads
+    const __nv_bfloat16 *Hhi, *Hlo;      // LayerNorm(X), split bf16, [T][128]
+    const __nv_bfloat16 *Whi, *Wlo;      // head-grouped Wqkv [4*96][128]
+    const float* bias;                   // head-grouped bqkv [4*96]
+    __nv_bfloat16 *out_hi, *out_lo;      // attention output, split bf16, [T][128] (may alias Hhi/Hlo: tile-local in-place)
+    uint32_t m_tiles;
+};
+cudaError_t qkv_attn_tc(const QkvAttnArgs& a, int num_sms, cudaStream_t st);
 struct StemArgs {  // k_stem_tc: the stem as a contraction over taps x 16 features (C == 128 only)
     const __nv_bfloat16 *Whi, *Wlo;  // W' [128][Kp], split bf16
     uint32_t Kp;                     // k_blocks * 64

@@ -619,6 +619,330 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused QKV projection + read-axis attention for C == 128, 4 heads of 32:
+//   per 128-token tile (4 positions x 32 read tokens) and head h:
+//     MMA(h):  acc[h][128 x 96] = H_tile · Wp[h]^T      Wp[h] = [Wq_h ; Wk_h ; Wv_h] (rows permuted at load), tcgen05
+//     ATT(h):  the warp that owns a position's 32 TMEM lanes reads q|k|v of its 32 tokens (lane = token) and runs the
+//              position's 32x32 attention entirely inside the warp: q, k, v are parked as split-bf16 rows in the warp's
+//              private shared-memory block, S = q·k^T and O = P·v run as warp-level mma.sync.m16n8k16 (operands by
+//              ldmatrix, bf16x3 like every other contraction here), softmax on the accumulator fragments in registers.
+//   tcgen05 cannot take these: its smallest M is 64 rows of ONE operand pair, but every 32-token position has its own
+//   K and V (a 128-row tile would be a block-diagonal product, 4x wasted, with P and V^T staged through shared memory);
+//   a first version with fp32 FFMA dot products out of shared memory was bound by the LSU (a broadcast LDS.128 costs two
+//   wavefronts per 4 FMAs per lane: 73 % of the shared-memory pipe, 2.4 ms per step) — ncu: profiles/r01d_*.
+//   The two compute warpgroups take alternate heads; the four heads have their own TMEM accumulators, so the MMAs and
+//   weight traffic run a whole tile ahead of the attention.  q, k, v never reach HBM: saves writing and re-reading the
+//   fp32 [T, 3C] tensor (3 KB per token and layer) and one kernel's fill/drain.
+// ------------------------------------------------------------------------------------------------
+constexpr int QA_HROWS = 96;                        // q|k|v rows of one head
+constexpr int QA_RING_BYTES = 2 * QA_HROWS * 128;   // one k-block of a head's weights, hi + lo: 24 KB
+constexpr int QA_STAGES = 3;
+constexpr int QA_WARP_BYTES = 8192;                 // per compute warp: 4 swizzled [32 rows][64 B] bf16 arrays
+constexpr uint32_t IDESC_N96 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(QA_HROWS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16_n96(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_N96), "r"(accumulate)
+        : "memory");
+}
+// single-lane waits of the producer / MMA warps: back off between polls so the spinning does not take issue slots
+// from the compute warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// [32 rows][32 bf16] array with 64-byte rows; the 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3), which makes the
+// row-owner 16-byte stores, the ldmatrix row fetches (8 rows, same chunk) and the staged output rows all bank-conflict free
+__device__ __forceinline__ uint32_t qa_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+// the lane's row of 32 fp32 values (TMEM words + bias, scaled) -> split bf16 -> its row of the hi and lo arrays
+__device__ __forceinline__ void qa_store_row(uint8_t* hi_arr, uint8_t* lo_arr, int lane, const uint32_t (&v)[32], const float* bias, float scale) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2)
+            split2((__uint_as_float(v[c * 8 + e]) + bias[c * 8 + e]) * scale, (__uint_as_float(v[c * 8 + e + 1]) + bias[c * 8 + e + 1]) * scale,
+                   hi[e >> 1], lo[e >> 1]);
+        const uint32_t off = qa_off(lane, c);
+        *(uint4*)(hi_arr + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *(uint4*)(lo_arr + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, const __grid_constant__ CUtensorMap tmHhi,
+                                                             const __grid_constant__ CUtensorMap tmHlo, const __grid_constant__ CUtensorMap tmWhi,
+                                                             const __grid_constant__ CUtensorMap tmWlo) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t* sA = smem;                                   // H tile: [kb][hi|lo][128 x 128 B]
+    uint8_t* ring = sA + FFN_A_BYTES;                     // QA_STAGES x QA_RING_BYTES
+    uint8_t* sW = ring + QA_STAGES * QA_RING_BYTES;       // [8 warps][QA_WARP_BYTES]
+    __shared__ uint64_t full_bar[QA_STAGES], empty_bar[QA_STAGES], a_full, a_empty, h_full[4], h_empty[4];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[4 * QA_HROWS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == G_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < QA_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a_full, 1); mbar_init(&a_empty, 1);
+        for (int a = 0; a < 4; a++) { mbar_init(&h_full[a], 1); mbar_init(&h_empty[a], G_EPI / 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 4 * QA_HROWS; i += G_THREADS) s_bias[i] = g.bias[i];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    // TMEM columns: head h accumulates in [h*128, h*128 + 96)
+
+    if (warp == G_PROD_WARP) {
+        if (lane == 0) {
+            uint32_t it_stage = 0, n_done = 0;
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                const int m0 = (int)(tile * BM);
+                mbar_wait_sleep(&a_empty, (n_done & 1) ^ 1);
+                mbar_arrive_expect_tx(&a_full, FFN_A_BYTES);
+                for (int kb = 0; kb < 2; kb++) {
+                    tma_load_2d(smem_u32(sA) + kb * (2 * BM * 128), &tmHhi, &a_full, kb * BK, m0);
+                    tma_load_2d(smem_u32(sA) + kb * (2 * BM * 128) + BM * 128, &tmHlo, &a_full, kb * BK, m0);
+                }
+                for (int h = 0; h < 4; h++)
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % QA_STAGES, ph = (it_stage / QA_STAGES) & 1;
+                        mbar_wait_sleep(&empty_bar[s], ph ^ 1);
+                        const uint32_t sb = smem_u32(ring + (size_t)s * QA_RING_BYTES);
+                        mbar_arrive_expect_tx(&full_bar[s], QA_RING_BYTES);
+                        tma_load_2d(sb, &tmWhi, &full_bar[s], kb * BK, h * QA_HROWS);
+                        tma_load_2d(sb + QA_HROWS * 128, &tmWlo, &full_bar[s], kb * BK, h * QA_HROWS);
+                    }
+            }
+        }
+    } else if (warp == G_MMA_WARP) {
+        if (lane == 0) {
+            uint32_t it_stage = 0, n_done = 0;
+            const uint32_t ab = smem_u32(sA);
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                mbar_wait_sleep(&a_full, n_done & 1);
+                for (int h = 0; h < 4; h++) {
+                    mbar_wait_sleep(&h_empty[h], (n_done & 1) ^ 1);  // the previous tile's head h has been read out of this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + h * BN;
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % QA_STAGES, ph = (it_stage / QA_STAGES) & 1;
+                        mbar_wait_sleep(&full_bar[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sb = smem_u32(ring + (size_t)s * QA_RING_BYTES);
+                        const uint64_t dAh = make_desc(ab + kb * (2 * BM * 128)), dAl = make_desc(ab + kb * (2 * BM * 128) + BM * 128);
+                        const uint64_t dBh = make_desc(sb), dBl = make_desc(sb + QA_HROWS * 128);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            mma_bf16_n96(tmem_d, dAh + adv, dBh + adv, (kb | k) ? 1u : 0u);
+                            mma_bf16_n96(tmem_d, dAl + adv, dBh + adv, 1u);
+                            mma_bf16_n96(tmem_d, dAh + adv, dBl + adv, 1u);
+                        }
+                        umma_commit(&empty_bar[s]);
+                    }
+                    umma_commit(&h_full[h]);
+                }
+                umma_commit(&a_empty);  // H tile no longer needed
+            }
+        }
+    } else {
+        // =============================== attention: 8 warps; warp & 3 = position of the tile, warp >> 2 = head parity ====
+        const int wq = warp & 3, wg = warp >> 2;
+        const int gq = lane >> 2, tq = lane & 3;   // mma fragment coordinates: row group, column pair
+        uint8_t* wb = sW + (size_t)warp * QA_WARP_BYTES;
+        uint8_t *aQh = wb, *aQl = wb + 2048, *aKh = wb + 4096, *aKl = wb + 6144;  // V (hi, lo) reuses the Q arrays, the output staging the K arrays
+        const uint32_t uQh = smem_u32(aQh), uQl = smem_u32(aQl), uKh = smem_u32(aKh), uKl = smem_u32(aKl);
+        const float scale_l2 = rsqrtf(32.f) * 1.4426950408889634f;  // 1/sqrt(dh) and log2(e): scores come out in the exp2 domain
+        uint32_t n_done = 0;
+        for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+            for (int hh = 0; hh < 2; hh++) {
+                const int h = hh * 2 + wg;
+                mbar_wait(&h_full[h], n_done & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + h * BN + ((uint32_t)(wq * 32) << 16);
+                const float* bb = s_bias + h * QA_HROWS;
+                {
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);        // q of this lane's token
+                    qa_store_row(aQh, aQl, lane, v, bb, scale_l2);
+                    tmem_ld32(taddr + 32, v);   // k
+                    qa_store_row(aKh, aKl, lane, v, bb + 32, 1.f);
+                }
+                __syncwarp();
+                // ---- S = q·k^T: [32 queries][32 keys] as 2 x 4 accumulator tiles of m16n8
+                float sacc[2][4][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) sacc[mt][nt][e] = 0.f;
+                {
+                    uint32_t qh[2][2][4], ql[2][2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++) {
+                            const uint32_t off = qa_off(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4));
+                            ldsm_x4(uQh + off, qh[mt][ks]);
+                            ldsm_x4(uQl + off, ql[mt][ks]);
+                        }
+#pragma unroll
+                    for (int ntp = 0; ntp < 2; ntp++)
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++) {
+                            uint32_t kh[4], kl[4];
+                            const uint32_t off = qa_off(ntp * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1));
+                            ldsm_x4(uKh + off, kh);
+                            ldsm_x4(uKl + off, kl);
+#pragma unroll
+                            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                                for (int j = 0; j < 2; j++) {
+                                    mma16816(sacc[mt][ntp * 2 + j], qh[mt][ks], kh[2 * j], kh[2 * j + 1]);
+                                    mma16816(sacc[mt][ntp * 2 + j], ql[mt][ks], kh[2 * j], kh[2 * j + 1]);
+                                    mma16816(sacc[mt][ntp * 2 + j], qh[mt][ks], kl[2 * j], kl[2 * j + 1]);
+                                }
+                        }
+                }
+                // ---- softmax over the 31 real keys (key 31 is the pad token).  A lane holds, for each of its 4 query rows
+                //      (gq + 8*i), the 8 keys {8*nt + 2*tq, +1}; the other 24 keys of a row are in the 3 neighbouring lanes.
+                float inv[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        if (tq == 3) sacc[mt][3][2 * hf + 1] = -INFINITY;
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) m = fmaxf(m, fmaxf(sacc[mt][nt][2 * hf], sacc[mt][nt][2 * hf + 1]));
+                        m = fmaxf(m, __shfl_xor_sync(HB_FULL, m, 1));
+                        m = fmaxf(m, __shfl_xor_sync(HB_FULL, m, 2));
+                        float l = 0.f;
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) {
+                            const float p0 = exp2f(sacc[mt][nt][2 * hf] - m), p1 = exp2f(sacc[mt][nt][2 * hf + 1] - m);
+                            sacc[mt][nt][2 * hf] = p0; sacc[mt][nt][2 * hf + 1] = p1;
+                            l += p0 + p1;
+                        }
+                        l += __shfl_xor_sync(HB_FULL, l, 1);
+                        l += __shfl_xor_sync(HB_FULL, l, 2);
+                        const int row = mt * 16 + hf * 8 + gq;
+                        inv[mt][hf] = (row < R_COLS) ? 1.f / l : 0.f;  // the pad token's output row is written as zeros
+                    }
+                // ---- v: read it out of TMEM only now (the Q arrays are free once every lane has its fragments)
+                __syncwarp();
+                {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 64, v);
+                    qa_store_row(aQh, aQl, lane, v, bb + 64, 1.f);
+                }
+                // the accumulator is drained: the MMAs of the next tile's head h may overwrite it
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&h_empty[h]);
+                __syncwarp();
+                // ---- O = P·v: P fragments come straight from the S accumulator layout (two n-tiles = one k16 A fragment)
+                float oacc[2][4][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int dt = 0; dt < 4; dt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) oacc[mt][dt][e] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                    uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        split2(sacc[mt][2 * ks][0], sacc[mt][2 * ks][1], ph[mt][0], pl[mt][0]);
+                        split2(sacc[mt][2 * ks][2], sacc[mt][2 * ks][3], ph[mt][1], pl[mt][1]);
+                        split2(sacc[mt][2 * ks + 1][0], sacc[mt][2 * ks + 1][1], ph[mt][2], pl[mt][2]);
+                        split2(sacc[mt][2 * ks + 1][2], sacc[mt][2 * ks + 1][3], ph[mt][3], pl[mt][3]);
+                    }
+#pragma unroll
+                    for (int dp = 0; dp < 2; dp++) {
+                        uint32_t vh[4], vl[4];
+                        const uint32_t off = qa_off(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4));
+                        ldsm_x4_trans(uQh + off, vh);
+                        ldsm_x4_trans(uQl + off, vl);
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                mma16816(oacc[mt][dp * 2 + j], ph[mt], vh[2 * j], vh[2 * j + 1]);
+                                mma16816(oacc[mt][dp * 2 + j], pl[mt], vh[2 * j], vh[2 * j + 1]);
+                                mma16816(oacc[mt][dp * 2 + j], ph[mt], vl[2 * j], vl[2 * j + 1]);
+                            }
+                    }
+                }
+                // ---- normalise, split, stage the 32 output rows (64 B of hi and of lo each) in the K arrays, store coalesced
+                uint32_t* sth = (uint32_t*)aKh;
+                uint32_t* stl = (uint32_t*)aKl;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        const int row = mt * 16 + hf * 8 + gq;
+#pragma unroll
+                        for (int dt = 0; dt < 4; dt++) {
+                            uint32_t hi, lo;
+                            split2(oacc[mt][dt][2 * hf] * inv[mt][hf], oacc[mt][dt][2 * hf + 1] * inv[mt][hf], hi, lo);
+                            const int w = row * 16 + ((dt ^ ((row >> 1) & 3)) << 2) + tq;
+                            sth[w] = hi;
+                            stl[w] = lo;
+                        }
+                    }
+                __syncwarp();
+                const size_t rb = ((size_t)tile * BM + wq * 32) * BN + h * 32;  // row 0 of this position, this head's columns
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
+                    const int w = rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2);
+                    *(uint4*)(g.out_hi + rb + (size_t)rr * BN + cq * 8) = *(const uint4*)(sth + w);
+                    *(uint4*)(g.out_lo + rb + (size_t)rr * BN + cq * 8) = *(const uint4*)(stl + w);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == G_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stem on the tensor cores: Embedding(12,6) ++ qual -> Conv(7->C, k=(K,1)) is linear in the one-hot
 // token and in the quality value, so per read token it is a contraction over K' = taps x 16 features
 // (11 one-hot token slots, q_hi, q_lo, 3 zero) with W'[c][j*16+f] = tab[j][f][c] / wq[j][c].  The A
@@ -859,12 +1183,12 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // 2-D bf16 tensor [rows][cols] with row stride `ld` elements; box = 128 rows x 64 columns (one SWIZZLE_128B k-block tile)
-static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows = BM) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t gdim[2] = {cols, rows};
     const cuuint64_t gstr[1] = {ld * 2};
-    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t box[2] = {BK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -906,6 +1230,24 @@ cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
         !make_tmap(&t1l, a.W1lo, a.F, BN, BN) || !make_tmap(&t2h, a.W2hi, BN, a.F, a.F) || !make_tmap(&t2l, a.W2lo, BN, a.F, a.F))
         return cudaErrorInvalidValue;
     k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l);
+    return cudaGetLastError();
+}
+
+cudaError_t qkv_attn_tc(const QkvAttnArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)FFN_A_BYTES + (size_t)QA_STAGES * QA_RING_BYTES + (size_t)8 * QA_WARP_BYTES + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_qkv_attn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.m_tiles == 0) return cudaSuccess;
+    CUtensorMap tHh, tHl, tWh, tWl;
+    const uint64_t T = (uint64_t)a.m_tiles * BM;
+    if (!make_tmap(&tHh, a.Hhi, T, BN, BN) || !make_tmap(&tHl, a.Hlo, T, BN, BN) || !make_tmap(&tWh, a.Whi, 4 * QA_HROWS, BN, BN, QA_HROWS) ||
+        !make_tmap(&tWl, a.Wlo, 4 * QA_HROWS, BN, BN, QA_HROWS))
+        return cudaErrorInvalidValue;
+    k_qkv_attn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, tWh, tWl);
     return cudaGetLastError();
 }
 

@@ -115,3 +115,20 @@ def test_lane_count_invariance(monkeypatch):
     b = helpers.run_product(rs, model, 4096, 64, launch_targets=4)
     assert a["segments"] == b["segments"]
     assert b["stats"]["device_launches"] >= 4
+
+
+def test_fused_qkv_attention_equals_unfused(monkeypatch):
+    """k_qkv_attn_ws (QKV projection + attention on chip; scores and P·V as bf16x3 mma.sync) against the separate
+    contraction + fp32 SIMT k_attention kernels: same emitted bases, logits equal to fp32 rounding noise."""
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=13)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    monkeypatch.setenv("HERRO_B200_NO_FUSE_ATTN", "1")
+    b = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    assert b["stats"]["kernel_launches"] > a["stats"]["kernel_launches"]
+    assert a["segments"] == b["segments"]
+    worst = 0.0
+    for key, wa in a["windows"].items():
+        wb = b["windows"][key]
+        worst = max(worst, float(np.abs(wa["bases_logits"] - wb["bases_logits"]).max(initial=0.0)))
+    assert worst <= 1e-4, worst
