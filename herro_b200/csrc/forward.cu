@@ -410,23 +410,32 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     if (T > (size_t)npos * TOK_PER_POS)
         cudaMemsetAsync(ws.X + (size_t)npos * TOK_PER_POS * C, 0, (T - (size_t)npos * TOK_PER_POS) * C * sizeof(float), st);
     const size_t stem_smem = ((wt.stem_k * 32 + 15) & ~15) + (size_t)wt.stem_k * 32 * 4;
+    const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
+    // With C == 128 a kernel that writes the residual stream owns whole rows in its epilogue, so the LayerNorm that
+    // follows is computed there (stem epilogue, GEMM_OUT_F32_RES_LN, fused FFN); k_layernorm is the fallback.
+    static const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid
+    const bool fuse_ln = (C == 128) && !no_fuse;
+    const bool stem_ln = fuse_ln && wt.stem_kblocks;
+    if (stem_ln && T > (size_t)npos * TOK_PER_POS) {  // rows of the pad positions: defined operands for the contractions
+        const size_t off = (size_t)npos * TOK_PER_POS * C, n = (T - (size_t)npos * TOK_PER_POS) * C;
+        cudaMemsetAsync(ws.Hhi + off, 0, n * sizeof(__nv_bfloat16), st);
+        cudaMemsetAsync(ws.Hlo + off, 0, n * sizeof(__nv_bfloat16), st);
+    }
     kt.begin(K_STEM);
     if (wt.stem_kblocks) {
         StemArgs sa{(const __nv_bfloat16*)wt.s_stem.hi, (const __nv_bfloat16*)wt.s_stem.lo, (uint32_t)wt.stem_kblocks * 64,
                     (uint32_t)wt.stem_kblocks, (uint32_t)wt.stem_k, wt.stem_b, wt.read_pos, ws.X, n0, npos};
+        if (stem_ln) { sa.ln_g = wt.layer[0].ln1_g; sa.ln_b = wt.layer[0].ln1_b; sa.out_hi = ws.Hhi; sa.out_lo = ws.Hlo; }
         stem_tc(b, sa, wt.num_sms, st);
     } else {
         k_stem<<<npos, (C + 31) / 32 * 32, stem_smem, st>>>(b, wt, n0, npos, ws.X);
     }
     kt.end(); nl++;
-    const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
-    // With C == 128 a contraction that writes the residual stream owns whole rows in its epilogue, so the
-    // LayerNorm that follows is computed there (GEMM_OUT_F32_RES_LN); only the first one needs a kernel.
-    static const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid
-    const bool fuse_ln = (C == 128) && !no_fuse;
-    kt.begin(K_LAYERNORM);
-    k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
-    kt.end(); nl++;
+    if (!stem_ln) {
+        kt.begin(K_LAYERNORM);
+        k_layernorm<<<ln_blocks, 256, 0, st>>>(ws.X, ws.Hhi, ws.Hlo, wt.layer[0].ln1_g, wt.layer[0].ln1_b, (uint32_t)T, C);
+        kt.end(); nl++;
+    }
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
         const bool no_fuse_attn = getenv("HERRO_B200_NO_FUSE_ATTN") != nullptr;  // debugging aid / A-B parity test

@@ -80,6 +80,8 @@ struct StemArgs {  // k_stem_tc: the stem as a contraction over taps x 16 featur
     const float *bias, *read_pos;    // [128], [31][128]
     float* X;                        // [positions*32][128]
     uint32_t n0, npos;               // work-list range
+    const float *ln_g = nullptr, *ln_b = nullptr;          // optional: LayerNorm(X) of every row, emitted as split bf16
+    __nv_bfloat16 *out_hi = nullptr, *out_lo = nullptr;    // [positions*32][128]; nullptr: X only
 };
 cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStream_t st);
 cudaError_t split_weights(const float* w, size_t n, void** hi, void** lo);

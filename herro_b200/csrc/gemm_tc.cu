@@ -962,8 +962,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_stage[4][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
+    __shared__ __align__(16) float s_bias[BN], s_lng[BN], s_lnb[BN];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < BN) {
+        s_bias[tid] = g.bias[tid];
+        s_lng[tid] = g.out_hi ? g.ln_g[tid] : 1.f;
+        s_lnb[tid] = g.out_hi ? g.ln_b[tid] : 0.f;
+    }
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -1095,38 +1101,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
             }
         }
     } else {
-        // =============================== epilogue: relu(acc + bias) + read_pos ===============================
+        // =============================== epilogue: relu(acc + bias) + read_pos (+ the first LayerNorm) ===============
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
             mbar_wait(&tfull_bar[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const size_t row = (size_t)item * BM + warp * 32 + lane;  // token row: position = item*4 + warp, read = lane
+            // token row: position = item*4 + warp, read = lane
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
             float* oblk = g.X + ((size_t)item * BM + warp * 32) * BN;  // this warp's 32 token rows
             const float* rp = g.read_pos + (size_t)(lane < R_COLS ? lane : 0) * BN;
-            (void)row;
-#pragma unroll 1
+            float x[BN];  // the thread's whole row: the LayerNorm statistics need no exchange
+#pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
-                float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *(const float4*)(g.bias + c0 + j);
+                    const float4 bv = *(const float4*)(s_bias + c0 + j);
                     const float4 pv = *(const float4*)(rp + c0 + j);
-                    o[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x; o[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y;
-                    o[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z; o[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w;
+                    x[c0 + j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x; x[c0 + j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y;
+                    x[c0 + j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z; x[c0 + j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w;
                 }
                 if (lane >= R_COLS) {  // the pad token of every position
 #pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] = 0.f;
+                    for (int j = 0; j < 32; j++) x[c0 + j] = 0.f;
                 }
-                warp_store_f32x16(s_stage[warp], lane, oblk + c0, BN, o);
-                warp_store_f32x16(s_stage[warp], lane, oblk + c0 + 16, BN, o + 16);
+                warp_store_f32x16(s_stage[warp], lane, oblk + c0, BN, x + c0);
+                warp_store_f32x16(s_stage[warp], lane, oblk + c0 + 16, BN, x + c0 + 16);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
+            if (g.out_hi) {
+                // LayerNorm of the row (layer 0's ln1) -> split bf16: the operand of the first QKV projection
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < BN; j++) sum += x[j];
+                const float mean = sum * (1.f / BN);
+                float var = 0.f;
+#pragma unroll
+                for (int j = 0; j < BN; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
+                const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
+                __nv_bfloat16* hblk = g.out_hi + ((size_t)item * BM + warp * 32) * BN;
+                __nv_bfloat16* lblk = g.out_lo + ((size_t)item * BM + warp * 32) * BN;
+#pragma unroll
+                for (int j = 0; j < BN; j += 16) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2)
+                        split2((x[j + e] - mean) * rstd * s_lng[j + e] + s_lnb[j + e], (x[j + e + 1] - mean) * rstd * s_lng[j + e + 1] + s_lnb[j + e + 1],
+                               hi[e >> 1], lo[e >> 1]);
+                    warp_store_bf16x16((uint32_t*)s_stage[warp], lane, hblk + j, BN, hi);
+                    warp_store_bf16x16((uint32_t*)s_stage[warp], lane, lblk + j, BN, lo);
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
