@@ -39,10 +39,15 @@ std::atomic<uint64_t> g_ctx_generation{1};  // the launch worker reports into it
 std::atomic<uint64_t> g_allocs{0}, g_alloc_ns{0}, g_submit_wait_ns{0};
 struct AllocScope {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* kind;
+    size_t bytes;
+    AllocScope(const char* k, size_t b) : kind(k), bytes(b) {}
     ~AllocScope() {
+        const uint64_t ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         g_allocs.fetch_add(1, std::memory_order_relaxed);
-        g_alloc_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
-                             std::memory_order_relaxed);
+        g_alloc_ns.fetch_add(ns, std::memory_order_relaxed);
+        static const bool dbg = getenv("HERRO_B200_DEBUG_ALLOC") != nullptr;
+        if (dbg) fprintf(stderr, "[herro_b200 alloc] %s %.1f MB %.2f ms\n", kind, (double)bytes / 1e6, (double)ns * 1e-6);
     }
 };
 
@@ -53,8 +58,8 @@ struct DevBuf {
                                 // cudaMalloc/cudaFree synchronise the whole device and would stall the other lanes
     cudaError_t ensure(size_t bytes, bool keep = false) {
         if (bytes <= cap) return cudaSuccess;
-        AllocScope as_;
         size_t ncap = bytes + bytes / 2 + 256;
+        AllocScope as_(st ? "device(stream-ordered)" : "device", ncap);
         void* np = nullptr;
         if (st) {
             cudaError_t e = cudaMallocAsync(&np, ncap, st);
@@ -80,7 +85,7 @@ struct PinBuf {
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        AllocScope as_;
+        AllocScope as_("pinned(lane)", bytes + bytes / 2 + 256);
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
@@ -112,8 +117,8 @@ struct PinVec {
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
     bool reserve(size_t want) {
         if (want <= cap) return true;
-        AllocScope as_;
         size_t ncap = (n == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
+        AllocScope as_("pinned(staging)", ncap * sizeof(T));
         T* np = nullptr;
         int cur = -1;
         if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) cudaSetDevice(dev);  // growth is rare: only then touch the runtime

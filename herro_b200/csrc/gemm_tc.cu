@@ -31,7 +31,6 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int STAGE_BYTES = (2 * BM + 2 * BN) * 128;  // A hi/lo + W hi/lo tiles of one k-block: 64 KB
-constexpr int NUM_EPI = 128, NUM_PROD = 128, NUM_THREADS = 288;  // k_stem_tc: warps 0-3 epilogue, 4-7 producers, 8 MMA
 // k_gemm_ws / k_ffn_ws: the epilogue is the critical path (4 warps could not keep up with the tensor pipe), so two
 // epilogue warpgroups split the 128 columns of an accumulator: warps 0-7 epilogue (warp & 3 = TMEM lane quadrant,
 // warp >> 2 = column half), warp 8 TMA producer, warp 9 MMA
@@ -953,16 +952,25 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
 // ------------------------------------------------------------------------------------------------
 constexpr int STEM_STAGE_BYTES = (BM + 2 * BN) * 128;  // A (hi only) + W' hi/lo tiles of one k-block: 48 KB
 constexpr int STEM_MAXK = 64;                           // taps supported by the staging buffers
+constexpr int STEM_RP_LD = 132;                         // row stride (floats) of the read_pos copy: conflict-free 16-byte rows per lane
+// warps 0-7 epilogue (warp & 3 = TMEM lane quadrant = position of the item, warp >> 2 = column half), 8-11 producers, 12 MMA
+constexpr int S_EPI = 256, S_PROD = 128, S_THREADS = 416, S_MMA_WARP = 12;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArgs g) {
+__global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs g, const __grid_constant__ CUtensorMap tmWhi,
+                                                         const __grid_constant__ CUtensorMap tmWlo) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t* tokbuf = smem + STAGES * STEM_STAGE_BYTES;          // [2][4 positions][STEM_MAXK taps][32] tokens
     uint8_t* qbuf = tokbuf + 2 * 4 * STEM_MAXK * 32;             // same shape, raw quality bytes
+    float* s_rp = (float*)(qbuf + 2 * 4 * STEM_MAXK * 32);       // read_pos [32][STEM_RP_LD] (row 31 = zeros)
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float s_stage[4][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
+    __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
     __shared__ __align__(16) float s_bias[BN], s_lng[BN], s_lnb[BN];
+    __shared__ float s_red[2][2][BM];                    // [item parity][column half][row]: LayerNorm partial sums
+    // A-operand synthesis tables: the 16 bf16 features of a token (one-hot slot), and (q_hi | q_lo << 16) of a quality byte
+    __shared__ __align__(16) uint4 s_lut[13][2];
+    __shared__ uint32_t s_qlut[256];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < BN) {
@@ -970,13 +978,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
         s_lng[tid] = g.out_hi ? g.ln_g[tid] : 1.f;
         s_lnb[tid] = g.out_hi ? g.ln_b[tid] : 0.f;
     }
-    if (warp == 8) {
+    if (tid < 256) {
+        const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
+        const float q = __fsub_rn(__fmul_rn((float)tid, QS), QO);
+        const __nv_bfloat16 qh = __float2bfloat16_rn(q);
+        const __nv_bfloat16 ql = __float2bfloat16_rn(q - __bfloat162float(qh));
+        s_qlut[tid] = (uint32_t)__bfloat16_as_ushort(qh) | ((uint32_t)__bfloat16_as_ushort(ql) << 16);
+    }
+    if (tid < 13) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tid < 11) w[tid >> 1] = (tid & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0 in feature slot `tid`
+        s_lut[tid][0] = make_uint4(w[0], w[1], w[2], w[3]);
+        s_lut[tid][1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    for (int i = tid; i < 32 * BN; i += S_THREADS) {
+        const int r = i >> 7, c = i & 127;
+        s_rp[r * STEM_RP_LD + c] = r < R_COLS ? g.read_pos[i] : 0.f;
+    }
+    if (warp == S_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], NUM_PROD); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], S_PROD + 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], S_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -987,19 +1012,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
     const uint32_t kbs = g.k_blocks;
     const int K = g.taps;
 
-    if (warp >= 4 && warp < 8) {
-        // =============================== producers ===============================
-        const int p = tid - 128;
-        const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
+    if (warp >= 8 && warp < 12) {
+        // =============================== producers: thread p synthesises row p of the A tile ===============================
+        const int p = tid - S_EPI;
+        const int pos = p >> 5, rd = p & 31;
         uint32_t it_stage = 0, n_done = 0;
-        int pending = -1;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             // ---- stage the K x 32 token / quality neighbourhood of the 4 positions of this item
             uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
             uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
-            for (int i = p; i < 4 * K * 2; i += NUM_PROD) {  // one 16-byte half row per iteration
-                const int pos = i / (K * 2), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
-                const uint32_t n = item * 4 + pos;
+            for (int i = p; i < 4 * K * 2; i += S_PROD) {  // one 16-byte half row per iteration
+                const int ps = i / (K * 2), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
+                const uint32_t n = item * 4 + ps;
                 uint4 tv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), qv = make_uint4(0, 0, 0, 0);
                 if (n < g.npos) {
                     const uint32_t w = b.fwd_win[g.n0 + n], r = b.fwd_row[g.n0 + n];
@@ -1016,64 +1040,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
                         }
                     }
                 }
-                *(uint4*)(tb + (pos * STEM_MAXK + j) * 32 + half * 16) = tv;
-                *(uint4*)(qb + (pos * STEM_MAXK + j) * 32 + half * 16) = qv;
+                *(uint4*)(tb + (ps * STEM_MAXK + j) * 32 + half * 16) = tv;
+                *(uint4*)(qb + (ps * STEM_MAXK + j) * 32 + half * 16) = qv;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");  // producers only
+            const uint8_t* trow = tb + pos * STEM_MAXK * 32 + rd;  // this row's token of tap j at trow[j * 32]
+            const uint8_t* qrow = qb + pos * STEM_MAXK * 32 + rd;
             for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
                 const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sA = smem + (size_t)s * STEM_STAGE_BYTES;
-                const uint32_t sb = smem_u32(sA);
-                // ---- W' k-block: 128 rows x 8 chunks, hi and lo
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int idx = i * 128 + p, r = idx >> 3, c = idx & 7;
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                    const size_t gw = (size_t)r * g.Kp + (size_t)kb * BK + c * 8;
-                    cp_async16(sb + BM * 128 + off, g.Whi + gw);
-                    cp_async16(sb + BM * 128 + BN * 128 + off, g.Wlo + gw);
+                if (p == 0) {  // W' k-block (hi, lo) by TMA
+                    mbar_arrive_expect_tx(&full_bar[s], 2 * BN * 128);
+                    tma_load_2d(smem_u32(sA) + BM * 128, &tmWhi, &full_bar[s], (int)(kb * BK), 0);
+                    tma_load_2d(smem_u32(sA) + BM * 128 + BN * 128, &tmWlo, &full_bar[s], (int)(kb * BK), 0);
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                // ---- A k-block: 4 taps x 16 features per row; (row, tap) items, 4 per thread
+                // ---- A k-block: 4 taps x 16 features of this row, looked up (one-hot token slot | quality columns)
+                uint32_t tk[4], qq[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int idx = i * 128 + p, r = idx >> 2, tl = idx & 3;  // row 0..127, tap-in-block 0..3
+                for (int tl = 0; tl < 4; tl++) {
                     const int j = (int)kb * 4 + tl;
-                    const int pos = r >> 5, rd = r & 31;
-                    uint32_t w16[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 16 bf16 features
-                    if (j < K && rd < R_COLS) {
-                        const uint8_t tok = tb[(pos * STEM_MAXK + j) * 32 + rd];
-                        if (tok != 0xff) {
-                            const uint32_t one = (tok & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0 in the odd / even half
+                    const bool in = (j < K) && (rd < R_COLS);
+                    tk[tl] = in ? (uint32_t)trow[j * 32] : 0xffu;
+                    qq[tl] = in ? (uint32_t)qrow[j * 32] : 0u;
+                }
 #pragma unroll
-                            for (int e = 0; e < 6; e++) w16[e] = (tok < 11 && (tok >> 1) == e) ? one : 0u;
-                            const float q = __fsub_rn(__fmul_rn((float)qb[(pos * STEM_MAXK + j) * 32 + rd], QS), QO);
-                            const __nv_bfloat16 qh = __float2bfloat16_rn(q);
-                            const __nv_bfloat16 ql = __float2bfloat16_rn(q - __bfloat162float(qh));
-                            w16[5] |= (uint32_t)__bfloat16_as_ushort(qh) << 16;  // feature 11
-                            w16[6] |= (uint32_t)__bfloat16_as_ushort(ql);        // feature 12
-                        }
+                for (int tl = 0; tl < 4; tl++) {
+                    const uint32_t idx = min(tk[tl], 12u);  // 0xff (row outside the reference batch / pad read) -> all zero
+                    uint4 w0 = s_lut[idx][0], w1 = s_lut[idx][1];
+                    if (idx < 12u) {
+                        const uint32_t qw = s_qlut[qq[tl]];
+                        w1.y |= qw << 16;      // feature 11 = q_hi
+                        w1.z |= qw >> 16;      // feature 12 = q_lo
                     }
-                    const int c0 = tl * 2;
-                    *(uint4*)(sA + (uint32_t)r * 128u + (uint32_t)(((c0) ^ (r & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
-                    *(uint4*)(sA + (uint32_t)r * 128u + (uint32_t)(((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl) ^ (p & 7)) << 4)) = w0;
+                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl + 1) ^ (p & 7)) << 4)) = w1;
                 }
-                // publish the previous stage (its cp.asyncs have had a stage's worth of time), keep this one pending
-                if (pending >= 0) {
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(&full_bar[pending]);
-                }
-                pending = (int)s;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full_bar[s]);
             }
         }
-        if (pending >= 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full_bar[pending]);
-        }
-    } else if (warp == 8) {
+    } else if (warp == S_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             uint32_t it_stage = 0, n_done = 0;
@@ -1100,25 +1107,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
                 umma_commit(&tfull_bar[acc]);
             }
         }
-    } else {
+    } else if (warp < 8) {
         // =============================== epilogue: relu(acc + bias) + read_pos (+ the first LayerNorm) ===============
+        const int wq = warp & 3, eh = warp >> 2, ch = eh * 64;
+        const float* rp = s_rp + lane * STEM_RP_LD + ch;   // row 31 (the pad token of every position) is zero
+        float* stg = s_stage[warp];
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
             mbar_wait(&tfull_bar[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // token row: position = item*4 + warp, read = lane
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16);
-            float* oblk = g.X + ((size_t)item * BM + warp * 32) * BN;  // this warp's 32 token rows
-            const float* rp = g.read_pos + (size_t)(lane < R_COLS ? lane : 0) * BN;
-            float x[BN];  // the thread's whole row: the LayerNorm statistics need no exchange
+            // token row: position = item*4 + wq, read = lane
+            const uint32_t r = wq * 32 + lane;
+            const uint32_t taddr = tmem_base + acc * BN + ch + ((uint32_t)(wq * 32) << 16);
+            float* xblk = g.X + ((size_t)item * BM + wq * 32) * BN + ch;  // this warp's [32 rows][64 cols] block of X
+            float x[64];
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *(const float4*)(s_bias + c0 + j);
+                    const float4 bv = *(const float4*)(s_bias + ch + c0 + j);
                     const float4 pv = *(const float4*)(rp + c0 + j);
                     x[c0 + j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f) + pv.x; x[c0 + j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f) + pv.y;
                     x[c0 + j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f) + pv.z; x[c0 + j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f) + pv.w;
@@ -1127,55 +1137,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_stem_tc(BatchView b, StemArg
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[c0 + j] = 0.f;
                 }
-                warp_store_f32x16(s_stage[warp], lane, oblk + c0, BN, x + c0);
-                warp_store_f32x16(s_stage[warp], lane, oblk + c0 + 16, BN, x + c0 + 16);
+                warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
             if (g.out_hi) {
-                // LayerNorm of the row (layer 0's ln1) -> split bf16: the operand of the first QKV projection
+                // LayerNorm of the row (layer 0's ln1) -> split bf16: the operand of the first QKV projection.
+                // Partial sums are exchanged with the thread that owns the other 64 columns of the row.
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < BN; j++) sum += x[j];
-                const float mean = sum * (1.f / BN);
+                for (int j = 0; j < 64; j++) sum += x[j];
+                s_red[acc][eh][r] = sum;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float mean = (s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN);
                 float var = 0.f;
 #pragma unroll
-                for (int j = 0; j < BN; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
-                const float rstd = rsqrtf(var * (1.f / BN) + 1e-5f);
-                __nv_bfloat16* hblk = g.out_hi + ((size_t)item * BM + warp * 32) * BN;
-                __nv_bfloat16* lblk = g.out_lo + ((size_t)item * BM + warp * 32) * BN;
+                for (int j = 0; j < 64; j++) { const float d = x[j] - mean; var = fmaf(d, d, var); }
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // both halves have read the sums
+                s_red[acc][eh][r] = var;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float rstd = rsqrtf((s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN) + 1e-5f);
+                __nv_bfloat16* hblk = g.out_hi + ((size_t)item * BM + wq * 32) * BN + ch;
+                __nv_bfloat16* lblk = g.out_lo + ((size_t)item * BM + wq * 32) * BN + ch;
 #pragma unroll
-                for (int j = 0; j < BN; j += 16) {
+                for (int j = 0; j < 64; j += 16) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int e = 0; e < 16; e += 2)
-                        split2((x[j + e] - mean) * rstd * s_lng[j + e] + s_lnb[j + e], (x[j + e + 1] - mean) * rstd * s_lng[j + e + 1] + s_lnb[j + e + 1],
-                               hi[e >> 1], lo[e >> 1]);
-                    warp_store_bf16x16((uint32_t*)s_stage[warp], lane, hblk + j, BN, hi);
-                    warp_store_bf16x16((uint32_t*)s_stage[warp], lane, lblk + j, BN, lo);
+                        split2((x[j + e] - mean) * rstd * s_lng[ch + j + e] + s_lnb[ch + j + e],
+                               (x[j + e + 1] - mean) * rstd * s_lng[ch + j + e + 1] + s_lnb[ch + j + e + 1], hi[e >> 1], lo[e >> 1]);
+                    warp_store_bf16x16((uint32_t*)stg, lane, hblk + j, BN, hi);
+                    warp_store_bf16x16((uint32_t*)stg, lane, lblk + j, BN, lo);
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == S_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
-}
-
-cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    const size_t smem = (size_t)STAGES * STEM_STAGE_BYTES + 2 * 2 * 4 * STEM_MAXK * 32 + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const uint32_t items = (a.npos + 3) / 4;
-    if (items == 0) return cudaSuccess;
-    k_stem_tc<<<(unsigned)std::min<uint32_t>(items, (uint32_t)num_sms), NUM_THREADS, smem, st>>>(b, a);
-    return cudaGetLastError();
 }
 
 // split fp32 values into bf16 hi / lo (weights at model load; the self test's activations)
@@ -1258,6 +1260,22 @@ cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
         !make_tmap(&t1l, a.W1lo, a.F, BN, BN) || !make_tmap(&t2h, a.W2hi, BN, a.F, a.F) || !make_tmap(&t2l, a.W2lo, BN, a.F, a.F))
         return cudaErrorInvalidValue;
     k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l);
+    return cudaGetLastError();
+}
+
+cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)STAGES * STEM_STAGE_BYTES + 2 * 2 * 4 * STEM_MAXK * 32 + (size_t)32 * STEM_RP_LD * 4 + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint32_t items = (a.npos + 3) / 4;
+    if (items == 0) return cudaSuccess;
+    CUtensorMap tWh, tWl;
+    if (!make_tmap(&tWh, a.Whi, BN, a.Kp, a.Kp) || !make_tmap(&tWl, a.Wlo, BN, a.Kp, a.Kp)) return cudaErrorInvalidValue;
+    k_stem_tc<<<(unsigned)std::min<uint32_t>(items, (uint32_t)num_sms), S_THREADS, smem, st>>>(b, a, tWh, tWl);
     return cudaGetLastError();
 }
 
