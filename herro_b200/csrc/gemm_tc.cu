@@ -954,7 +954,8 @@ constexpr int STEM_STAGE_BYTES = (BM + 2 * BN) * 128;  // A (hi only) + W' hi/lo
 constexpr int STEM_MAXK = 64;                           // taps supported by the staging buffers
 constexpr int STEM_RP_LD = 132;                         // row stride (floats) of the read_pos copy: conflict-free 16-byte rows per lane
 // warps 0-7 epilogue (warp & 3 = TMEM lane quadrant = position of the item, warp >> 2 = column half), 8-11 producers, 12 MMA
-constexpr int S_EPI = 256, S_PROD = 128, S_THREADS = 416, S_MMA_WARP = 12;
+// 13-14 gather (token/quality neighbourhoods from the pileup matrix, one item ahead)
+constexpr int S_EPI = 256, S_PROD = 128, S_GATHER = 64, S_THREADS = 480, S_MMA_WARP = 12;
 
 __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs g, const __grid_constant__ CUtensorMap tmWhi,
                                                          const __grid_constant__ CUtensorMap tmWlo) {
@@ -963,7 +964,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
     uint8_t* tokbuf = smem + STAGES * STEM_STAGE_BYTES;          // [2][4 positions][STEM_MAXK taps][32] tokens
     uint8_t* qbuf = tokbuf + 2 * 4 * STEM_MAXK * 32;             // same shape, raw quality bytes
     float* s_rp = (float*)(qbuf + 2 * 4 * STEM_MAXK * 32);       // read_pos [32][STEM_RP_LD] (row 31 = zeros)
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2], buf_full[2], buf_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
     __shared__ __align__(16) float s_bias[BN], s_lng[BN], s_lnb[BN];
@@ -1001,7 +1002,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], S_PROD + 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], S_EPI); }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], S_EPI);
+            mbar_init(&buf_full[a], S_GATHER); mbar_init(&buf_empty[a], S_PROD);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1018,32 +1022,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
         const int pos = p >> 5, rd = p & 31;
         uint32_t it_stage = 0, n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
-            // ---- stage the K x 32 token / quality neighbourhood of the 4 positions of this item
-            uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
-            uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
-            for (int i = p; i < 4 * K * 2; i += S_PROD) {  // one 16-byte half row per iteration
-                const int ps = i / (K * 2), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
-                const uint32_t n = item * 4 + ps;
-                uint4 tv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), qv = make_uint4(0, 0, 0, 0);
-                if (n < g.npos) {
-                    const uint32_t w = b.fwd_win[g.n0 + n], r = b.fwd_row[g.n0 + n];
-                    const uint32_t L = b.w_L[w], Lref = b.w_reflmax[w];
-                    const int64_t row = (int64_t)r + j - K / 2;
-                    if (row >= 0 && row < (int64_t)Lref) {
-                        if (row < (int64_t)L) {
-                            const uint64_t off = (b.w_rowbase[w] + row) * ROW_BYTES + half * 16;
-                            tv = *(const uint4*)(b.mat_bases + off);
-                            qv = *(const uint4*)(b.mat_quals + off);
-                        } else {  // batch padding row of the reference's collate: token 11, qual byte 126
-                            tv = make_uint4(0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu);
-                            qv = make_uint4(0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu);
-                        }
-                    }
-                }
-                *(uint4*)(tb + (ps * STEM_MAXK + j) * 32 + half * 16) = tv;
-                *(uint4*)(qb + (ps * STEM_MAXK + j) * 32 + half * 16) = qv;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // producers only
+            const uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            const uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            mbar_wait(&buf_full[n_done & 1], (n_done >> 1) & 1);  // the gather warps have staged this item's neighbourhood
             const uint8_t* trow = tb + pos * STEM_MAXK * 32 + rd;  // this row's token of tap j at trow[j * 32]
             const uint8_t* qrow = qb + pos * STEM_MAXK * 32 + rd;
             for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
@@ -1079,6 +1060,48 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&full_bar[s]);
             }
+            mbar_arrive(&buf_empty[n_done & 1]);  // the staging buffer may be refilled
+        }
+    } else if (warp > S_MMA_WARP) {
+        // =============================== gather warps: stage the K x 32 token / quality neighbourhood of the 4 positions of
+        // an item (double buffered, one item ahead of the synthesis, so the dependent global loads are off its critical path)
+        const int gt = tid - (S_MMA_WARP + 1) * 32;  // 0..63
+        uint32_t n_done = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+            uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            // per-position metadata: lane l < 4 loads it for position l, every lane gets it by shuffle
+            uint32_t m_row = 0, m_L = 0, m_Lref = 0;
+            uint64_t m_base = 0;
+            if (lane < 4 && item * 4 + lane < g.npos) {
+                const uint32_t w = b.fwd_win[g.n0 + item * 4 + lane];
+                m_row = b.fwd_row[g.n0 + item * 4 + lane];
+                m_L = b.w_L[w]; m_Lref = b.w_reflmax[w]; m_base = b.w_rowbase[w];
+            }
+            mbar_wait(&buf_empty[n_done & 1], ((n_done >> 1) & 1) ^ 1);
+            for (int i0 = 0; i0 < 4 * K * 2; i0 += S_GATHER) {  // one 16-byte half row per iteration (warp-uniform trip count)
+                const int i = i0 + gt;
+                const int ps = min(i / (K * 2), 3), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
+                const uint32_t r = __shfl_sync(HB_FULL, m_row, ps), L = __shfl_sync(HB_FULL, m_L, ps), Lref = __shfl_sync(HB_FULL, m_Lref, ps);
+                const uint64_t rbase = __shfl_sync(HB_FULL, m_base, ps);
+                uint4 tv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), qv = make_uint4(0, 0, 0, 0);
+                const int64_t row = (int64_t)r + j - K / 2;
+                if (row >= 0 && row < (int64_t)Lref) {  // Lref == 0 for positions past the work list
+                    if (row < (int64_t)L) {
+                        const uint64_t off = (rbase + row) * ROW_BYTES + half * 16;
+                        tv = *(const uint4*)(b.mat_bases + off);
+                        qv = *(const uint4*)(b.mat_quals + off);
+                    } else {  // batch padding row of the reference's collate: token 11, qual byte 126
+                        tv = make_uint4(0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu, 0x0b0b0b0bu);
+                        qv = make_uint4(0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu, 0x7e7e7e7eu);
+                    }
+                }
+                if (i < 4 * K * 2) {
+                    *(uint4*)(tb + (ps * STEM_MAXK + j) * 32 + half * 16) = tv;
+                    *(uint4*)(qb + (ps * STEM_MAXK + j) * 32 + half * 16) = qv;
+                }
+            }
+            mbar_arrive(&buf_full[n_done & 1]);
         }
     } else if (warp == S_MMA_WARP) {
         // =============================== MMA issuer ===============================
