@@ -70,6 +70,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                  "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
                  : "memory");
 }
+// pull a line towards L2 ahead of the (latency-exposed) row-owner loads of an epilogue
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -138,6 +140,26 @@ __device__ __forceinline__ void warp_store_f32x16(float* stg, int lane, float* g
     for (int jj = 0; jj < 4; jj++) {
         const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
         *(float4*)(gbase + (size_t)rr * ld + cq * 4) = *(const float4*)(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
+    }
+    __syncwarp();
+}
+// the two halves of warp_load_f32x16, so that the global loads of the next block can be in flight while the current one is
+// consumed: warp_ldg_f32x16 issues the 4 coalesced 16-byte loads, warp_xpose_f32x16 turns them into the lane's own row
+__device__ __forceinline__ void warp_ldg_f32x16(int lane, const float* gbase, size_t ld, float4 (&t)[4]) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) t[jj] = *(const float4*)(gbase + (size_t)(jj * 8 + (lane >> 2)) * ld + (lane & 3) * 4);
+}
+__device__ __forceinline__ void warp_xpose_f32x16(float* stg, int lane, const float4 (&t)[4], float* v) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        const int rr = jj * 8 + (lane >> 2), cq = lane & 3;
+        *(float4*)(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2)) = t[jj];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int cq = 0; cq < 4; cq++) {
+        const float4 u = *(const float4*)(stg + lane * 16 + ((cq ^ ((lane >> 1) & 3)) << 2));
+        v[cq * 4] = u.x; v[cq * 4 + 1] = u.y; v[cq * 4 + 2] = u.z; v[cq * 4 + 3] = u.w;
     }
     __syncwarp();
 }
@@ -256,13 +278,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
         const int wq = warp & 3, eh = warp >> 2;  // TMEM lane quadrant, column half
         const int ch = eh * 64;                   // first of this thread's 64 columns inside the 128-wide item
         if (g.mode == GEMM_OUT_F32_RES_LN && tid < BN) { s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
+        if ((g.mode == GEMM_OUT_F32_RES_LN || g.mode == GEMM_OUT_F32_RES) && blockIdx.x < n_items) {
+            const uint32_t fm0 = (blockIdx.x / g.n_chunks) * BM, fn0 = (blockIdx.x % g.n_chunks) * BN;
+            const float* pr = g.res + ((size_t)fm0 + wq * 32 + lane) * g.ldc + fn0 + ch;
+            prefetch_l2(pr); prefetch_l2(pr + 32);
+        }
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t m0 = (item / g.n_chunks) * BM, n0 = (item % g.n_chunks) * BN;
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+            if ((g.mode == GEMM_OUT_F32_RES_LN || g.mode == GEMM_OUT_F32_RES) && item + gridDim.x < n_items) {
+                // the residual rows of the next item: in L2 by the time its epilogue loads them (thread = row, 64 columns = 2 lines)
+                const uint32_t nm0 = ((item + gridDim.x) / g.n_chunks) * BM, nn0 = ((item + gridDim.x) % g.n_chunks) * BN;
+                const float* pr = g.res + ((size_t)nm0 + (warp & 3) * 32 + lane) * g.ldc + nn0 + (warp >> 2) * 64;
+                prefetch_l2(pr); prefetch_l2(pr + 32);
+            }
             if (tid < BN) s_bias[acc][tid] = g.bias[n0 + tid];  // the previous user of this slot finished 2 items ago
             asm volatile("bar.sync 2, 256;" ::: "memory");       // epilogue warps only
             const float* sb = s_bias[acc] + ch;
+            float4 pre[4];  // residual block in flight (software pipelined: the next block loads while this one is consumed)
+            if (g.mode == GEMM_OUT_F32_RES_LN)  // the first one is requested before the wait for the MMAs: it does not depend on them
+                warp_ldg_f32x16(lane, g.out + ((size_t)m0 + wq * 32) * g.ldc + ch, g.ldc, pre);
             mbar_wait(&tfull_bar[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t r = wq * 32 + lane;
@@ -281,7 +317,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_ws(GemmArgs g, const __gr
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         float rv[16];
-                        warp_load_f32x16(stg, lane, xblk + c0 + h * 16, g.ldc, rv);
+                        warp_xpose_f32x16(stg, lane, pre, rv);
+                        if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, g.ldc, pre);
 #pragma unroll
                         for (int j = 0; j < 16; j++) x[c0 + h * 16 + j] = __uint_as_float(v[h * 16 + j]) + sb[c0 + h * 16 + j] + rv[j];
                         warp_store_f32x16(stg, lane, xblk + c0 + h * 16, g.ldc, x + c0 + h * 16);
@@ -524,6 +561,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
             const uint32_t r = wq * 32 + lane;
             const size_t row = (size_t)tile * BM + r;
+            {   // the residual rows this thread adds in the final epilogue (~10 us from now): start them towards L2
+                const float* pr = g.X + row * BN + ch;
+                prefetch_l2(pr); prefetch_l2(pr + 32);
+            }
             for (int c = 0; c < 4; c++) {
                 // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major; this thread's 64 columns = k-block eh)
                 const uint32_t j = c & 1;
@@ -559,6 +600,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             }
             // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16 (partial sums exchanged between the halves)
             const uint32_t oacc = n_done & 1;
+            float4 pre[4];  // first residual block: requested before the wait for the last MMAs (it does not depend on them)
+            warp_ldg_f32x16(lane, g.X + ((size_t)tile * BM + wq * 32) * BN + ch, BN, pre);
             mbar_wait(&o_full[oacc], (n_done >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ch + ((uint32_t)(wq * 32) << 16);
@@ -572,7 +615,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     float rv[16];
-                    warp_load_f32x16(stg, lane, xblk + c0 + h * 16, BN, rv);
+                    warp_xpose_f32x16(stg, lane, pre, rv);
+                    if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, BN, pre);
 #pragma unroll
                     for (int jj = 0; jj < 16; jj++)
                         x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_b2[ch + c0 + h * 16 + jj] + rv[jj];
