@@ -287,24 +287,34 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        mk, nk = st_full["ms_kernel"], st_full["n_kernel"]
-        top = max(mk, key=lambda k: mk[k])
-        gemm_tf = st_full["gemm_flops"] / (mk["gemm"] * 1e-3) / 1e12 if mk["gemm"] > 0 else 0.0
+        mk, nk, cf = st_full["ms_kernel"], st_full["n_kernel"], st_full["class_flops"]
+        # the dominant kernel of the step, by CUDA-event time of the isolated full-size launch
+        KERNEL_OF = {"gemm": "k_gemm_ws", "ffn": "k_ffn_ws", "qkv_attn": "k_qkv_attn_ws", "stem": "k_stem_tc", "pileup": "k_pass2b"}
+        DESCR = {"gemm": "tcgen05 bf16x3 contractions: out-proj(+LN) and read-axis collapse",
+                 "ffn": "fused FFN1 -> ReLU -> FFN2 + residual + LayerNorm on tcgen05, bf16x3",
+                 "qkv_attn": "fused QKV projection (tcgen05) + read-axis attention (mma.sync), bf16x3",
+                 "stem": "embedding+conv stem as a tcgen05 contraction (2 passes) + first LayerNorm",
+                 "pileup": "pileup build (tile in shared memory, second get_supported, majority vote)"}
+        top = max((k for k in mk if k in KERNEL_OF), key=lambda k: mk[k])
         pile_gbs = st_full["pileup_algo_bytes"] / (mk["pileup"] * 1e-3) / 1e9 if mk["pileup"] > 0 else 0.0
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
         except Exception:
             pass
-        t_gemm = traffic.get("k_gemm_ws", {}).get("dram_bytes_per_launch")
-        t_pile = traffic.get("k_pass2b", {}).get("dram_bytes_per_launch")
-        if top == "gemm":
-            roof = {"kernel": "k_gemm_ws (tcgen05 bf16x3 contractions of the forward; algorithmic fp32 FLOPs, 3 MMA passes each)",
-                    "bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
-                    "traffic": t_gemm, "traffic_note": "avg DRAM bytes per k_gemm_ws launch, profiles/r01b_traffic.json", "peak_source": peak_src}
+        t_top = traffic.get(KERNEL_OF[top], {}).get("dram_bytes_per_launch")
+        if top == "pileup":
+            roof = {"kernel": "k_pass2b (" + DESCR[top] + ")", "bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": pile_gbs / hbm_peak, "traffic": t_top, "peak_source": peak_src,
+                    "launches_per_step": nk[top], "ms_per_launch": mk[top] / max(nk[top], 1)}
         else:
-            roof = {"kernel": "k_pass2b (pileup build)", "bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": pile_gbs / hbm_peak, "traffic": t_pile, "peak_source": peak_src}
+            tf = cf[top] / (mk[top] * 1e-3) / 1e12
+            roof = {"kernel": KERNEL_OF[top] + " (" + DESCR[top] + "; algorithmic fp32 FLOPs over 31 read tokens per position, "
+                    "each executed as 3 bf16 MMA passes)", "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": tf / tf_peak, "traffic": t_top, "traffic_note": "avg DRAM bytes per launch, profiles/r01d_traffic.json",
+                    "peak_source": peak_src, "launches_per_step": nk[top], "ms_per_launch": mk[top] / max(nk[top], 1)}
+        tensor_classes = {k: {"ms": mk[k], "launches": nk[k], "algorithmic_tflops": cf[k] / (mk[k] * 1e-3) / 1e12}
+                          for k in ("stem", "qkv_attn", "gemm", "ffn") if nk.get(k) and mk[k] > 0}
         out = {
             "metric": METRIC, "value": bases_dev / t_dev, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -324,6 +334,7 @@ def main():
             "gpu_launches": int(st["kernel_launches"] + st2["kernel_launches"]),
             "roofline": roof,
             "kernels_ms_per_step": {k: mk[k] for k in mk if nk[k]},
+            "tensor_kernels": tensor_classes,
             "pileup_roofline": {"bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pile_gbs / hbm_peak},
             "clocks": sampler.summary(),
         }

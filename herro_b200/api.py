@@ -38,7 +38,7 @@ class HbOptions(C.Structure):
 
 
 KERNEL_CLASSES = ["tokenize", "pass1", "scores", "pass2a", "scan", "pileup", "lists", "stem", "layernorm", "gemm",
-                  "attention", "heads", "consensus"]
+                  "attention", "heads", "consensus", "ffn", "qkv_attn"]
 
 
 class HbStats(C.Structure):
@@ -50,7 +50,7 @@ class HbStats(C.Structure):
                [(n, C.c_uint64) for n in ("last_launch_targets", "last_launch_windows", "last_launch_bases")] + \
                [("ms_worker_busy", C.c_double), ("ms_worker_gpu_wait", C.c_double)] + \
                [("host_allocs", C.c_uint64), ("ms_host_alloc", C.c_double), ("ms_submit_wait", C.c_double),
-                ("ms_worker_phase", C.c_double * 8)]
+                ("class_flops", C.c_uint64 * 16), ("ms_worker_phase", C.c_double * 8)]
 
 
 HOST_LIB_PATH = os.path.join(_HERE, "libherro_host.so")
@@ -270,7 +270,8 @@ class Context:
     def stats(self) -> dict:
         s = HbStats()
         self._check(self._L.hb_get_stats(self._h, C.byref(s)))
-        d = {n: getattr(s, n) for n, _ in HbStats._fields_ if n not in ("ms_kernel", "n_kernel", "ms_worker_phase")}
+        d = {n: getattr(s, n) for n, _ in HbStats._fields_ if n not in ("ms_kernel", "n_kernel", "ms_worker_phase", "class_flops")}
+        d["class_flops"] = {k: int(s.class_flops[i]) for i, k in enumerate(KERNEL_CLASSES)}
         d["ms_worker_phase"] = [float(x) for x in s.ms_worker_phase]
         d["ms_kernel"] = {k: s.ms_kernel[i] for i, k in enumerate(KERNEL_CLASSES)}
         d["n_kernel"] = {k: int(s.n_kernel[i]) for i, k in enumerate(KERNEL_CLASSES)}

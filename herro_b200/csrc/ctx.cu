@@ -655,6 +655,9 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         const uint64_t ff = forward_flops_per_pos(ctx->wt, &gf);
         S.forward_flops += ff * n_sup;
         S.gemm_flops += gf * n_sup;
+        uint64_t cf[16];
+        forward_class_flops_per_pos(ctx->wt, cf);
+        for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) S.class_flops[i] += cf[i] * n_sup;
     }
 
     // ---- per-read reassembly (src/consensus.rs:90-111,222-226)
@@ -735,7 +738,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         T.d2h_bytes += S.d2h_bytes; T.kernel_launches += S.kernel_launches; T.device_launches += S.device_launches;
         T.pileup_algo_bytes += S.pileup_algo_bytes; T.gemm_flops += S.gemm_flops; T.forward_flops += S.forward_flops;
         T.ms_features += S.ms_features; T.ms_forward += S.ms_forward; T.ms_consensus += S.ms_consensus;
-        for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) { T.ms_kernel[i] += S.ms_kernel[i]; T.n_kernel[i] += S.n_kernel[i]; }
+        for (int i = 0; i < HB_NUM_KERNEL_CLASSES; i++) { T.ms_kernel[i] += S.ms_kernel[i]; T.n_kernel[i] += S.n_kernel[i]; T.class_flops[i] += S.class_flops[i]; }
         S.ms_worker_phase[6] = now_ms() - t_mark;
         for (int i = 0; i < 8; i++) T.ms_worker_phase[i] += S.ms_worker_phase[i];
         for (auto& r : out_results) ctx->results.push_back(std::move(r));

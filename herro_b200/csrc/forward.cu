@@ -398,6 +398,19 @@ uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops) {
     return stem + g + (uint64_t)wt.layers * per_layer_attn + heads;
 }
 
+static bool attn_is_fused(const FwdWeights& wt) { return wt.layer[0].bqkvp && getenv("HERRO_B200_NO_FUSE_ATTN") == nullptr; }
+void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]) {
+    const uint64_t C = wt.C, F = wt.F, D = wt.D, K = wt.stem_k, S = R_COLS, dh = wt.C / wt.H, L = wt.layers;
+    for (auto& o : out) o = 0;
+    out[K_STEM] = S * K * 7 * C * 2;
+    const uint64_t qkv = S * 2 * C * 3 * C, attn = (uint64_t)wt.H * 2 * 2 * S * S * dh, oproj = S * 2 * C * C, ffn = S * 2 * 2 * C * F;
+    if (attn_is_fused(wt)) out[K_QKV_ATTN] = L * (qkv + attn);
+    else { out[K_GEMM] += L * qkv; out[K_ATTENTION] = L * attn; }
+    out[K_GEMM] += L * oproj + 2 * S * C * D;
+    if (ffn_is_fused(wt)) out[K_FFN] = L * ffn; else out[K_GEMM] += L * ffn;
+    out[K_HEADS] = 2 * D * 6;
+}
+
 // Runs positions [n0, n0+npos) of the work list.  Returns the number of kernel launches.
 int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, uint8_t* wsb,
                          float* logits, float* info, cudaStream_t st, KTimer& kt) {
@@ -438,12 +451,11 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     }
     for (int l = 0; l < wt.layers; l++) {
         const FwdLayer& ly = wt.layer[l];
-        const bool no_fuse_attn = getenv("HERRO_B200_NO_FUSE_ATTN") != nullptr;  // debugging aid / A-B parity test
-        if (ly.bqkvp && !no_fuse_attn) {
+        if (attn_is_fused(wt)) {  // HERRO_B200_NO_FUSE_ATTN: debugging aid / A-B parity test
             // QKV projection + attention in one kernel (q, k, v stay on chip); output over the LN buffers, tile-local in-place
             QkvAttnArgs qa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_qkvp.hi, (const __nv_bfloat16*)ly.s_qkvp.lo, ly.bqkvp, ws.Hhi, ws.Hlo,
                            (uint32_t)(T / 128)};
-            kt.begin(K_ATTENTION); qkv_attn_tc(qa, wt.num_sms, st); kt.end(); nl++;
+            kt.begin(K_QKV_ATTN); qkv_attn_tc(qa, wt.num_sms, st); kt.end(); nl++;
         } else {
             gemm(wt, GEMM_OUT_F32, ws.Hhi, ws.Hlo, C, ly.s_qkv, ly.bqkv, ws.QKV, nullptr, 3 * C, nullptr, nullptr, 0, T, 3 * C, C, st, kt); nl++;
             // attention writes its (split) output over the LN buffers: the QKV contraction has consumed them (stream order)
@@ -469,7 +481,7 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
             FfnArgs fa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_1.hi, (const __nv_bfloat16*)ly.s_1.lo,
                        (const __nv_bfloat16*)ly.s_2.hi, (const __nv_bfloat16*)ly.s_2.lo, ly.b1, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo,
                        (uint32_t)F, (uint32_t)(T / 128)};
-            kt.begin(K_GEMM); ffn_tc(fa, wt.num_sms, st); kt.end(); nl++;
+            kt.begin(K_FFN); ffn_tc(fa, wt.num_sms, st); kt.end(); nl++;
             continue;
         }
         gemm(wt, GEMM_OUT_SPLIT_RELU, ws.Hhi, ws.Hlo, C, ly.s_1, ly.b1, nullptr, nullptr, 0, ws.Fhi, ws.Flo, F, T, F, C, st, kt); nl++;

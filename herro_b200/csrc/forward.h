@@ -125,12 +125,14 @@ struct KTimer {
     void destroy() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
 };
 enum { K_TOKENIZE = 0, K_PASS1, K_SCORES, K_PASS2A, K_SCAN, K_PILEUP, K_LISTS, K_STEM, K_LAYERNORM, K_GEMM, K_ATTENTION,
-       K_HEADS, K_CONSENSUS };
+       K_HEADS, K_CONSENSUS, K_FFN, K_QKV_ATTN };
 
 size_t fwd_workspace_bytes(const FwdWeights& wt, uint32_t chunk_pos);
 int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, uint32_t npos, uint8_t* ws,
                          float* logits, float* info, cudaStream_t st, KTimer& kt);
 uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops);
+// algorithmic FLOPs per supported position attributed to the kernel class that executes them on the active code path
+void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]);
 
 // features.cu
 cudaError_t features_configure(uint32_t W);

@@ -136,7 +136,8 @@ const char* hb_last_error(hb_ctx* ctx); /* ctx may be NULL: error of a failed hb
 #define HB_NUM_KERNEL_CLASSES 16
 /* kernel classes of ms_kernel[] / n_kernel[] */
 enum { HB_K_TOKENIZE = 0, HB_K_PASS1, HB_K_SCORES, HB_K_PASS2A, HB_K_SCAN, HB_K_PILEUP, HB_K_LISTS, HB_K_STEM,
-       HB_K_LAYERNORM, HB_K_GEMM, HB_K_ATTENTION, HB_K_HEADS, HB_K_CONSENSUS };
+       HB_K_LAYERNORM, HB_K_GEMM, HB_K_ATTENTION, HB_K_HEADS, HB_K_CONSENSUS,
+       HB_K_FFN /* fused FFN kernel */, HB_K_QKV_ATTN /* fused QKV projection + attention kernel */ };
 typedef struct hb_stats {
     uint64_t targets, windows, overlap_windows, rows, supported, corrected_bases;
     uint64_t h2d_bytes, d2h_bytes, kernel_launches, device_launches /* batches */;
@@ -152,6 +153,7 @@ typedef struct hb_stats {
     uint64_t host_allocs;    /* page-locked / device allocations made since the last reset (0 in steady state)  */
     double ms_host_alloc;    /* wall time spent in them                                                         */
     double ms_submit_wait;   /* wall time hb_submit_* callers were blocked on back-pressure (summed over threads) */
+    uint64_t class_flops[HB_NUM_KERNEL_CLASSES]; /* algorithmic FLOPs (31 read tokens per supported position) by kernel class */
     double ms_worker_phase[8]; /* launch-worker wall time by phase: 0 buffers+H2D enqueue, 1 feature launches,
                                   2 wait (row counts), 3 forward+consensus launches, 4 wait (results),
                                   5 per-read reassembly, 6 publish                                               */

@@ -41,8 +41,15 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def _raw(src):
+    """raw page of a .ncu-rep, or a CSV already exported with `ncu -i x.ncu-rep --page raw --csv` (large reports stay on the GPU box)"""
+    if src.endswith(".csv"):
+        return open(src).read()
+    return subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = _raw(src)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [(m, hdr.index(m)) for m in METRICS if m in hdr]
@@ -55,5 +62,27 @@ def full(src, dst):
     print(open(dst).read()[:3000])
 
 
+def traffic(src, dst, note=""):
+    """per-kernel DRAM traffic (read + write) averaged over the captured launches -> JSON read by bench.py"""
+    import json
+    raw = _raw(src)
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ik, ir, iw, it = (hdr.index(m) for m in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ik])
+        a = agg[name]
+        a[0] += 1
+        a[1] += float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+        a[2] += float(r[it].replace(",", "")) * tscale[units[it]]
+    out = {k: {"launches_captured": v[0], "dram_bytes_per_launch": v[1] / v[0], "ms_per_launch_under_ncu": v[2] / v[0]} for k, v in agg.items()}
+    out["_note"] = note
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
