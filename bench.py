@@ -40,7 +40,7 @@ UNIT = "bases/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10000)
@@ -247,6 +247,7 @@ def main():
     # and it is the launch the HBM-resident replay re-runs
     ctx.reset_stats()
     ctx.set_launch_targets(lt)
+    ctx.set_kernel_timing(True)
     for t in range((n_steps - 1) * lt, n_steps * lt):
         k = t - args.warmup * lt
         ctx.submit_target(t, (int(rs.off[t + 1] - rs.off[t]) + args.window - 1) // args.window,

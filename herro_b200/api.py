@@ -86,6 +86,7 @@ def load_library():
     L.hb_extract_windows.argtypes = [vp, u32, u32, u32, vp, u32, u32p]
     L.hb_flush.argtypes = [vp]
     L.hb_set_launch_targets.argtypes = [vp, u32]
+    L.hb_set_kernel_timing.argtypes = [vp, C.c_int]
     L.hb_poll_corrected.argtypes = [vp, u32p, C.POINTER(vp), C.POINTER(vp), u32p]
     L.hb_release_result.argtypes = [vp, vp]
     L.hb_release_result.restype = None
@@ -100,7 +101,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_set_launch_targets", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -236,6 +237,9 @@ class Context:
 
     def set_launch_targets(self, n: int):
         self._check(self._L.hb_set_launch_targets(self._h, n))
+
+    def set_kernel_timing(self, on: bool):
+        self._check(self._L.hb_set_kernel_timing(self._h, 1 if on else 0))
 
     def poll(self):
         """-> Corrected or None; raises HerroError for a target the reference would have panicked on."""

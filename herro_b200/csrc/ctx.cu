@@ -254,6 +254,7 @@ struct hb_ctx {
     bool idle() const { return queue.empty() && busy == 0; }
     size_t cap_hint[5] = {0, 0, 0, 0, 0};  // largest batch array sizes seen (tgt, win, ovl, ow, cig)
     std::atomic<uint32_t> n_slots{0};       // submitting threads registered since the last flush
+    std::atomic<bool> time_kernels{false};  // hb_set_kernel_timing
     uint64_t alloc_base[3] = {0, 0, 0};     // g_allocs / g_alloc_ns / g_submit_wait_ns at the last hb_reset_stats
     uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
 };
@@ -584,7 +585,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
     BatchView b;
     uint64_t total_rows = 0;
     PHASE(0);
-    L->kt.on = true;
+    L->kt.on = ctx->time_kernels.load(std::memory_order_relaxed);
     L->kt.st = L->stream;
     for (int attempt = 0;; attempt++) {
         if (attempt) L->kt.discard();
@@ -1114,6 +1115,12 @@ int hb_set_launch_targets(hb_ctx* ctx, uint32_t launch_targets) {
     if (!ctx || launch_targets == 0) return HB_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->opt.launch_targets = launch_targets;
+    return HB_OK;
+}
+
+int hb_set_kernel_timing(hb_ctx* ctx, int on) {
+    if (!ctx) return HB_ERR_ARG;
+    ctx->time_kernels.store(on != 0);
     return HB_OK;
 }
 

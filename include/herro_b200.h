@@ -116,6 +116,11 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
  * submissions.  Call between hb_flush and the next hb_submit_*. */
 int hb_set_launch_targets(hb_ctx* ctx, uint32_t launch_targets);
 
+/* Per-kernel CUDA-event timing (hb_stats.ms_kernel / n_kernel) for subsequent launches: off by default, because
+ * the two event records around each of the ~25 kernels of a launch cost device time; bench.py switches it on
+ * for the one isolated launch its roofline is computed from.  Stage-level times (ms_features, ...) are always kept. */
+int hb_set_kernel_timing(hb_ctx* ctx, int on);
+
 /* Launch whatever is pending (every feature thread stages its own batch) and wait until every submitted
  * target has a result queued.  Call it once the submitting threads are quiescent (the reference's
  * equivalent is the alignment channel closing, src/lib.rs:186); it must not race with hb_submit_*. */
