@@ -132,3 +132,21 @@ def test_fused_qkv_attention_equals_unfused(monkeypatch):
         wb = b["windows"][key]
         worst = max(worst, float(np.abs(wa["bases_logits"] - wb["bases_logits"]).max(initial=0.0)))
     assert worst <= 1e-4, worst
+
+
+@pytest.mark.parametrize("env", ["HERRO_B200_NO_FUSE_FFN", "HERRO_B200_NO_FUSE_LN"])
+def test_fused_ffn_and_layernorm_equal_unfused(monkeypatch, env):
+    """k_ffn_ws (hidden activations on chip, LayerNorm in the epilogue) / the LayerNorm-fused epilogues against the
+    chain of separate contraction and LayerNorm kernels: same emitted bases, logits equal to fp32 rounding noise."""
+    rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=14)
+    model = helpers.model_path(seed=3)
+    a = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    monkeypatch.setenv(env, "1")
+    b = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
+    assert b["stats"]["kernel_launches"] > a["stats"]["kernel_launches"]
+    assert a["segments"] == b["segments"]
+    worst = 0.0
+    for key, wa in a["windows"].items():
+        wb = b["windows"][key]
+        worst = max(worst, float(np.abs(wa["bases_logits"] - wb["bases_logits"]).max(initial=0.0)))
+    assert worst <= 1e-4, worst
