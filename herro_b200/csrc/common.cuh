@@ -158,6 +158,15 @@ struct QView {
         return rev ? (code_at(words, qe - 1u - x) ^ 3u) : code_at(words, qs + x);
     }
     __device__ __forceinline__ uint8_t q(uint32_t x) const { return rev ? __ldg(qual + (qe - 1u - x)) : __ldg(qual + qs + x); }
+    // q(x) .. q(x+3) as one little-endian word (all four offsets must lie inside the slice): two aligned word loads and a
+    // funnel shift; the aligned pair may reach 3 bytes before / 4 bytes past the four bytes, which stays inside the store
+    // (its base is 256-byte aligned and it is padded at the end).
+    __device__ __forceinline__ uint32_t q4(uint32_t x) const {
+        const uint8_t* a = rev ? qual + (qe - 4u - x) : qual + qs + x;
+        const uint32_t* aw = (const uint32_t*)((uintptr_t)a & ~(uintptr_t)3);
+        const uint32_t w = __funnelshift_r(__ldg(aw), __ldg(aw + 1), (uint32_t)((uintptr_t)a & 3u) * 8u);
+        return rev ? __byte_perm(w, 0u, 0x0123u) : w;
+    }
     // 32 oriented bases starting at oriented offset x (groups beyond the slice are unspecified)
     __device__ __forceinline__ uint64_t chunk(uint32_t x) const {
         if (!rev) return extract32(words, qs + x);

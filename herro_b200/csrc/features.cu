@@ -251,22 +251,23 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
             atomicAdd(&dcg[b.ow_tend[owi]], 0xffffffffu);
         }
         for (uint32_t k = lane; k < nops; k += 32) {
-            const uint32_t kl = b.op_kl[ow.op_base + k];
+            // the three op words are independent loads: issue them together (this loop is bound by load latency)
+            const uint32_t kl = b.op_kl[ow.op_base + k], t0 = b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
             const uint32_t kind = kl & 3u, eff = kl >> 2;
             if (kind == OP_I) continue;
-            const uint32_t t0 = b.op_t[ow.op_base + k];
             if (kind == OP_D) {
                 atomicAdd(&dcg[t0], 0x10000u);
                 atomicAdd(&dcg[t0 + eff], 0xffff0000u);
                 continue;
             }
-            const uint32_t q0 = b.op_q[ow.op_base + k];
+            uint64_t qc_next = qv.chunk(q0);
             for (uint32_t i = 0; i < eff; i += 32) {
                 const uint32_t p = t0 + i;
                 // target chunk from the staged window: 32 bases at window-relative position p
                 const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
                 const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
-                const uint64_t qc = qv.chunk(q0 + i);
+                const uint64_t qc = qc_next;
+                if (i + 32 < eff) qc_next = qv.chunk(q0 + i + 32);  // next chunk's words in flight while this one's mismatches are counted
                 uint64_t mm = mismatch_groups(tc, qc, eff - i);
                 while (mm) {
                     const int g2 = __ffsll((long long)mm) - 1;  // bit index 2g
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
     uint32_t* op_stage = (uint32_t*)(q_stage + 8 * QSTAGE);  // [8 warps][3][OPCAP] staged ops of the column-tile
     __shared__ uint32_t c_ow[32], c_rs[32], c_re[32], c_gap[32];
     __shared__ uint32_t s_phi, s_warp[8], s_nsup;
+    __shared__ uint32_t s_khint[8][4];  // per (warp, column slot): where the previous tile's op search ended
 
     const uint32_t w = blockIdx.x;
     const DevWin win = b.win[w];
@@ -522,6 +524,7 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
         c_ow[tid] = owi; c_rs[tid] = rs; c_re[tid] = re; c_gap[tid] = gap;
     }
     if (tid == 0) s_nsup = 0;
+    if (tid < 32) s_khint[tid >> 2][tid & 3] = 0;
 
     uint32_t p_lo = 0;
     __syncthreads();
@@ -600,31 +603,38 @@ __global__ void __launch_bounds__(256) k_pass2b(BatchView b) {
                 const uint32_t add = qv.rev ? 5u : 0u;
                 uint8_t* pt = p_tok + c * TR;
                 uint8_t* pq = p_q + c * TR;
-                // first op whose target span ends after p_lo (warp-uniform binary search on op_t)
-                uint32_t lo_k = 0, hi_k = nops;
-                while (lo_k < hi_k) {
-                    const uint32_t mid = (lo_k + hi_k) >> 1;
-                    if (opt[mid] < p_lo) lo_k = mid + 1; else hi_k = mid;
+                // first op with op_t >= p_lo.  op_t is sorted and p_lo grows from tile to tile, so the search resumes at the
+                // previous tile's answer for this column and probes 32 ops per step (one coalesced load, one ballot): the
+                // former warp-uniform binary searches were ~7 dependent global loads each, 13 % of the kernel's stall samples.
+                uint32_t lo_k;
+                for (uint32_t base = s_khint[warp][s_];; base += 32) {  // invariant: every op before `base` has op_t < p_lo
+                    const uint32_t idx = base + lane;
+                    const uint32_t m = __ballot_sync(HB_FULL, idx >= nops || opt[idx] >= p_lo);
+                    if (m) { lo_k = min(base + (uint32_t)__ffs(m) - 1u, nops); break; }
                 }
                 uint32_t k_first = lo_k;  // first op with op_t >= p_lo ...
                 if (k_first > 0) k_first--;  // ... and the one before it, which may straddle p_lo
+                if (lane == 0) s_khint[warp][s_] = k_first;
                 const uint32_t qbase = k_first < nops ? opq[k_first] : 0;  // oriented offset where the staged window starts
                 const uint32_t qslice = ow.qend - ow.qstart;
                 // ... and where it ends: the query offset of the first op that starts after the tile's positions
-                uint32_t lo_e = k_first, hi_e = nops;
-                while (lo_e < hi_e) {
-                    const uint32_t mid = (lo_e + hi_e) >> 1;
-                    if (opt[mid] <= p_hi) lo_e = mid + 1; else hi_e = mid;
+                uint32_t lo_e;  // first op in [k_first, nops) with op_t > p_hi, same probing
+                for (uint32_t base = k_first;; base += 32) {
+                    const uint32_t idx = base + lane;
+                    const uint32_t m = __ballot_sync(HB_FULL, idx >= nops || opt[idx] > p_hi);
+                    if (m) { lo_e = min(base + (uint32_t)__ffs(m) - 1u, nops); break; }
                 }
                 const uint32_t qend_t = lo_e < nops ? opq[lo_e] : qslice;
                 const uint32_t qn = min((uint32_t)QSTAGE, qend_t > qbase ? qend_t - qbase : 0u);
-                for (uint32_t i0 = 0; i0 < qn; i0 += 256) {  // 8 independent byte loads in flight per lane
-                    uint8_t v[8];
+                const uint32_t qn4 = qn >> 2;                      // whole 4-byte words of the staged window
+                for (uint32_t w0 = 0; w0 < qn4; w0 += 128) {       // 4 independent word fetches in flight per lane
+                    uint32_t v[4];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * 32 + lane; v[u] = i < qn ? qv.q(qbase + i) : 0; }
+                    for (int u = 0; u < 4; u++) { const uint32_t wi = w0 + u * 32 + lane; v[u] = wi < qn4 ? qv.q4(qbase + 4 * wi) : 0; }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * 32 + lane; if (i < qn) qst[i] = v[u]; }
+                    for (int u = 0; u < 4; u++) { const uint32_t wi = w0 + u * 32 + lane; if (wi < qn4) ((uint32_t*)qst)[wi] = v[u]; }
                 }
+                for (uint32_t i = 4 * qn4 + lane; i < qn; i += 32) qst[i] = qv.q(qbase + i);  // the last 0..3 bytes
                 // stage the ops that touch this tile (k_first .. lo_e) so that the lanes' searches and walks read shared memory
                 const uint32_t ne = min(nops, lo_e + 1) - k_first;
                 if (ne <= (uint32_t)OPCAP) {
