@@ -62,8 +62,7 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
 #pragma unroll
             for (int s = 1; s <= 10; s++) {
                 const int pc = __shfl_up_sync(HB_FULL, c, s);
-                const bool pd = __shfl_up_sync(HB_FULL, (int)is_digit, s) != 0;
-                const bool ok = (lane >= s) && pd;
+                const bool ok = (lane >= s) && pc >= '0' && pc <= '9';  // bytes outside the slice were loaded as 0
                 if (!stop && ok) {
                     num += (uint32_t)(pc - '0') * mul;
                     mul *= 10u;
@@ -71,6 +70,8 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
                 } else {
                     stop = true;
                 }
+                // op lengths rarely have more than 3 digits: leave as soon as every letter of this step has its number
+                if (s >= 2 && !__any_sync(HB_FULL, is_letter && !stop)) break;
             }
             const uint32_t mask = __ballot_sync(HB_FULL, is_letter);
             if (is_letter) {
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
                     const uint32_t p = t0 + i;
                     const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
                     const uint64_t sc = sh ? ((sup2[wi] >> sh) | (sup2[wi + 1] << (64u - sh))) : sup2[wi];
-                    if (!sc) continue;
+                    if (!sc) continue;  // no supported position among these 32: the query words are not even fetched
                     const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
                     const uint64_t mm = mismatch_groups(tc, qv.chunk(q0 + i), eff - i);
                     n += (uint32_t)__popcll(sc & valid_groups(eff - i) & ~mm);
