@@ -59,34 +59,61 @@ def parse():
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons of the job's GPUs DURING the timed region (B200_PROFILING.md).  One sampler for the whole
+    job (rank 0), through NVML in-process: a poller per rank spawning nvidia-smi five times a second contends for the driver
+    with the very launches being timed (measured at N=4).  Falls back to nvidia-smi when pynvml is unavailable."""
 
-    def __init__(self, index):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index = index
+        self.indices = list(indices)
         self.stop_flag = threading.Event()
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.n = 0
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        hs = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+        while not self.stop_flag.is_set():
+            for h in hs:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.reasons |= {name for bit, name in self.REASONS.items() if r & bit}
+            self.n += 1
+            self.stop_flag.wait(0.1)
+
+    def _smi_loop(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        ids = ",".join(str(i) for i in self.indices)
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", f"--id={ids}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for line in out.splitlines():
+                    r = [x.strip() for x in line.split(",")]
+                    if len(r) >= 6 and r[0].replace(".", "").isdigit():
+                        self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                        self.reasons |= {names[i] for i in range(4) if r[2 + i].lower().startswith("active")}
+                self.n += 1
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.5)
+
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": self.n,
+                "gpus": self.indices}
 
 
 def make_readset(args, rank):
@@ -231,8 +258,9 @@ def main():
     harness.run(0, args.warmup * lt, nthr, win_warm)
     ctx.replay_last_launch(1)
     ctx.reset_stats()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(range(args.gpus) if rank == 0 else [])
+    if rank == 0:
+        sampler.start()
     # ---- region 1: end to end through the C ABI, host buffers, copies inside: hb_submit_target from the
     #      feature threads (batch i+1 is staged while batch i is on the GPU), hb_poll_corrected from the consumer.
     barrier()
@@ -263,7 +291,8 @@ def main():
     ms_dev = ctx.replay_last_launch(args.steps)
     barrier()
     sampler.stop_flag.set()
-    sampler.join(timeout=3)
+    if rank == 0:
+        sampler.join(timeout=3)
     st2 = ctx.stats()
     # the replay re-runs the LAST timed launch `steps` times; its output size is known from region 1
     per_step_bases = last_launch_bases
@@ -274,9 +303,15 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = vals.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        gathered = [torch.zeros_like(vals) for _ in range(args.gpus)]
+        dist.all_gather(gathered, vals)
+        per_rank = {"ms_per_step": [round(1e3 * float(g[0]) / args.steps, 3) for g in gathered],
+                    "bases_per_step": [float(g[2]) / args.steps for g in gathered],
+                    "e2e_seconds": [round(float(g[1]), 4) for g in gathered]}
         t_dev, t_e2e = float(tmax[0]), float(tmax[1])
         bases_dev, bases_e2e_all = float(tsum[2]), float(tsum[3])
     else:
+        per_rank = None
         bases_dev, bases_e2e_all = float(vals[2]), float(vals[3])
 
     if rank == 0:
@@ -338,6 +373,7 @@ def main():
             "tensor_kernels": tensor_classes,
             "pileup_roofline": {"bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pile_gbs / hbm_peak},
             "clocks": sampler.summary(),
+            "per_rank": per_rank,  # each rank corrects its own read cluster: `value` = sum of bases / slowest rank's time
         }
         if not args.no_cpu_baseline and args.gpus == 1:
             tg = list(range(args.warmup * lt, args.warmup * lt + args.cpu_sample))
