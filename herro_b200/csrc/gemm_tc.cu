@@ -9,13 +9,18 @@
 // Weights are split once at load; activations are produced already split by the kernel that
 // writes them (LayerNorm, attention, the FFN1 epilogue), so operand staging is pure copying.
 //
-// Kernel: persistent, warp-specialised, 288 threads:
-//   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes (one position = 32 read tokens each),
-//              bias / ReLU / residual / bf16 split, 16-byte stores
-//   warps 4-7  producers: cp.async 16-byte chunks of A and W k-blocks into a 3-stage ring of
-//              K-major SWIZZLE_128B tiles (chunk c of row r at chunk c ^ (r & 7))
-//   warp  8    one lane issues tcgen05.mma (M=128, N=128, K=16; 12 per k-block), tcgen05.commit
-//              releases ring stages and publishes the accumulator
+// Kernels (all persistent, warp-specialised, one CTA per SM; operands as K-major SWIZZLE_128B shared-memory tiles):
+//   k_gemm_ws      D = A·W^T with bias / ReLU / residual / LayerNorm epilogues (out-proj, read-axis collapse, fallbacks)
+//   k_ffn_ws       FFN1 -> ReLU -> FFN2 + residual + LayerNorm, hidden activations kept on chip
+//   k_qkv_attn_ws  QKV projection (tcgen05) + per-position attention (mma.sync) in the epilogue warps
+//   k_stem_tc      embedding + conv stem as a contraction, A tile synthesised from the pileup matrix, + first LayerNorm
+// Common skeleton (k_gemm_ws, 320 threads):
+//   warps 0-7  two epilogue warpgroups: warp & 3 = TMEM lane quadrant (one position = 32 read tokens), warp >> 2 = column
+//              half; tcgen05.ld, bias / ReLU / residual / LayerNorm / bf16 split; global accesses transposed through
+//              per-warp shared-memory buffers so every instruction covers whole row segments
+//   warp  8    one lane issues TMA (cp.async.bulk.tensor.2d) for the A and W k-block tiles into a 3-stage ring
+//   warp  9    one lane issues tcgen05.mma (M=128, N=128, K=16; 12 per k-block), tcgen05.commit releases ring stages and
+//              publishes the accumulator
 // Two TMEM accumulators (2 x 128 columns) let the epilogue of item i overlap the MMAs of i+1.
 // Work items (m_tile, n_chunk) are dealt round-robin so CTAs working on the same m_tile share
 // its A tile in L2.
