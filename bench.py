@@ -125,6 +125,7 @@ def make_readset(args, rank):
     return rs, time.time() - t0
 
 
+_CACHE = {}
 _TUNED = {}  # host threads -> torch intra-op threads chosen by the probe in cpu_reference_run
 
 
@@ -135,9 +136,12 @@ def cpu_reference_run(rs, model, targets, window, batch_size, threads):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po, forward_ref
     from herro_b200 import weights as hbw
-    reads = po.Reads(rs.ids, [rs.seq(i) for i in range(rs.n)], [rs.qual(i) for i in range(rs.n)])
-    cfg, tensors = hbw.load_blob(model)
-    net = forward_ref.from_weights(cfg, tensors)
+    if _CACHE.get("rs") is not rs:  # the oracle's read store and the torch module are built once per read set / model
+        _CACHE.update(rs=rs, reads=po.Reads(rs.ids, [rs.seq(i) for i in range(rs.n)], [rs.qual(i) for i in range(rs.n)]))
+    if _CACHE.get("model") != model:
+        cfg, tensors = hbw.load_blob(model)
+        _CACHE.update(model=model, net=forward_ref.from_weights(cfg, tensors))
+    reads, net = _CACHE["reads"], _CACHE["net"]
 
     def feat(t):
         ovl, cigs = rs.target_alns(t)
