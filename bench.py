@@ -344,6 +344,7 @@ def main():
         per_rank = None
         bases_dev, bases_e2e_all = float(vals[2]), float(vals[3])
 
+    parity_failed = False
     if rank == 0:
         peaks = {}
         try:
@@ -408,12 +409,25 @@ def main():
         if not args.no_cpu_baseline and args.gpus == 1:
             tg = list(range(args.warmup * lt, args.warmup * lt + args.cpu_sample))
             r = cpu_reference_run(rs, model, tg, args.window, args.batch_size, threads)
+            # parity on the measured workload: the same targets through the CUDA path, segment for segment
+            ctx.set_kernel_timing(False)
+            for t in tg:
+                if rs.aln_off[t + 1] > rs.aln_off[t]:
+                    ctx.submit_alignments(t, harness.ovl[int(rs.aln_off[t]):int(rs.aln_off[t + 1])])
+            ctx.flush()
+            gpu_seg = {c.rid: (c.segments or None) for c in ctx.drain()}
+            same = all(gpu_seg.get(t) == r["segments"].get(t) for t in set(gpu_seg) | set(r["segments"]))
+            out["parity_sample"] = {"targets": len(tg), "identical": bool(same),
+                                    "bases": int(sum(len(x) for v in r["segments"].values() for x in (v or [])))}
+            parity_failed = not same
             out["cpu_baseline"] = {"value": r["bases"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{len(tg)} target reads of the workload; features {r['t_features']:.1f}s, "
                                              f"forward {r['t_forward']:.1f}s ({r['torch_threads']} torch threads, fastest of a probe), "
                                              f"consensus {r['t_consensus']:.2f}s"}
         print(json.dumps(out))
     ctx.close()
+    if rank == 0 and parity_failed:
+        raise SystemExit("parity_sample: the CUDA path and the CPU oracle disagree on the sampled targets")
     try:
         os.remove(model)
     except OSError:

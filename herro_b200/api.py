@@ -90,6 +90,7 @@ def load_library():
     L.hb_poll_corrected.argtypes = [vp, u32p, C.POINTER(vp), C.POINTER(vp), u32p]
     L.hb_release_result.argtypes = [vp, vp]
     L.hb_release_result.restype = None
+    L.hb_bind_calling_thread.argtypes = [vp]
     L.hb_get_stats.argtypes = [vp, C.POINTER(HbStats)]
     L.hb_reset_stats.argtypes = [vp]
     L.hb_debug_window_shape.argtypes = [vp, u32, u32, u32p]
@@ -101,7 +102,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -173,6 +174,7 @@ class Context:
         self.window_size = window_size
         self._keep = []
         self.read_len = None
+        self.failed = []
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -241,8 +243,12 @@ class Context:
     def set_kernel_timing(self, on: bool):
         self._check(self._L.hb_set_kernel_timing(self._h, 1 if on else 0))
 
+    def bind_calling_thread(self) -> bool:
+        return self._check(self._L.hb_bind_calling_thread(self._h)) == 1
+
     def poll(self):
-        """-> Corrected or None; raises HerroError for a target the reference would have panicked on."""
+        """-> Corrected or None; raises HerroError (with .rid) for a target that failed (e.g. one the reference would
+        have panicked on); the other targets are unaffected and polling can continue."""
         rid = C.c_uint32()
         seqs, seg_len = C.c_void_p(), C.c_void_p()
         n = C.c_uint32()
@@ -251,7 +257,9 @@ class Context:
             return None
         try:
             if rc < 0:
-                raise HerroError(rc, self._L.hb_last_error(self._h).decode())
+                e = HerroError(rc, self._L.hb_last_error(self._h).decode())
+                e.rid = rid.value
+                raise e
             lens = np.ctypeslib.as_array(C.cast(seg_len, C.POINTER(C.c_uint32)), (max(n.value, 1),))[:n.value].copy()
             segs, o = [], 0
             for l in lens:
@@ -262,10 +270,18 @@ class Context:
             if seqs.value:
                 self._L.hb_release_result(self._h, seqs)
 
-    def drain(self):
+    def drain(self, skip_failed: bool = False):
+        """All queued results.  skip_failed: a failed target is recorded in `self.failed` as (rid, code, message) and the
+        drain goes on (one bad read must not truncate the output of a whole run)."""
         out = []
         while True:
-            r = self.poll()
+            try:
+                r = self.poll()
+            except HerroError as e:
+                if not skip_failed:
+                    raise
+                self.failed.append((getattr(e, "rid", None), e.code, str(e)))
+                continue
             if r is None:
                 return out
             out.append(r)
@@ -350,7 +366,7 @@ class HostHarness:
 
     def run(self, t_begin: int, t_end: int, threads: int, windows=None) -> dict:
         H = _host_lib()
-        out3 = np.zeros(3, dtype=np.uint64)
+        out3 = np.zeros(4, dtype=np.uint64)
         chk = C.c_uint64()
         sec = C.c_double()
         sub = C.c_double()
@@ -360,8 +376,8 @@ class HostHarness:
                        self.ctx.window_size, t_begin, t_end, threads, ow_p, off_p, out3.ctypes.data, C.byref(chk), C.byref(sec), C.byref(sub))
         if rc != 0:
             raise HerroError(rc, self.ctx._L.hb_last_error(self.ctx._h).decode())
-        return dict(bases=int(out3[0]), records=int(out3[1]), targets=int(out3[2]), checksum=int(chk.value), seconds=sec.value,
-                    submit_seconds_sum=sub.value)
+        return dict(bases=int(out3[0]), records=int(out3[1]), targets=int(out3[2]), failed=int(out3[3]), checksum=int(chk.value),
+                    seconds=sec.value, submit_seconds_sum=sub.value)
 
 
 # ------------------------------------------------------------------------------------------

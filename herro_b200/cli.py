@@ -119,10 +119,12 @@ def inference(args):
             ctxs[k % len(ctxs)].submit_alignments(tid, api.Context.make_overlaps(ovl9, cig, coff))
         for c in ctxs:
             c.flush()
-            for r in c.drain():
+            for r in c.drain(skip_failed=True):
                 if r.segments:
                     out.write(api.fasta_records(ids[r.rid], descs[r.rid], r.segments))
                     n_rec += len(r.segments)
+            for rid, code, msg in c.failed:  # the reference would have aborted the whole run here; log the read and go on
+                print(f"skipped read {ids[rid].decode() if rid is not None else '?'}: {msg}", file=sys.stderr)
     print(f"Processed {len(alns)} reads, wrote {n_rec} records.", file=sys.stderr)
 
 

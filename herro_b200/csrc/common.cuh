@@ -8,7 +8,8 @@ namespace hb {
 constexpr int R_COLS = 31;        // TOP_K_SORT + 1 (src/features.rs:22)
 constexpr int ROW_BYTES = 32;     // internal row pitch of the [L',31] matrices (col 31 = pad)
 constexpr int TOP_K = 30;
-constexpr int MAX_COLS = 1024;    // overlap-windows per window handled on-chip (error beyond)
+constexpr int MAX_COLS = 1024;    // overlap-windows per window whose sort keys fit in shared memory (HBM scratch beyond)
+constexpr int MAX_COLS_HARD = 60000;  // 16-bit per-position counters in k_pass1: HB_ERR_CAPACITY beyond
 
 constexpr uint32_t TOK_GAP_F = 4, TOK_GAP_R = 9, TOK_NONE = 10, TOK_PAD = 11;  // src/inference.rs:15,23-31
 constexpr uint8_t QUAL_EMPTY = 33;    // '!' src/features.rs:283
@@ -78,6 +79,9 @@ struct BatchView {
     uint32_t* ow_tend;  // window-relative target position after the last op
     // per window, pass 1
     uint32_t* col_ow;  // [n_ow] first-pass column order (CSR with win.ow_begin)
+    float* big_key;    // [n_ow] sort scratch of windows with more than MAX_COLS overlap-windows
+    uint32_t* big_cand;
+    double* big_score;
     uint32_t* w_n1;    // columns surviving the filter
     uint32_t* w_S;     // first-pass supported base rows
     // per overlap (= per query read of a target)

@@ -21,6 +21,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include "../../include/herro_b200.h"
 #include "common.cuh"
 #include "forward.h"
@@ -76,6 +79,18 @@ struct DevBuf {
         cap = ncap;
         return cudaSuccess;
     }
+    // grow to exactly `ncap` bytes without headroom (pre-sizing an idle lane from another lane's sizes); contents are not kept
+    cudaError_t reserve_exact(size_t ncap) {
+        if (ncap <= cap) return cudaSuccess;
+        AllocScope as_(st ? "device(stream-ordered, presize)" : "device(presize)", ncap);
+        void* np = nullptr;
+        cudaError_t e = st ? cudaMallocAsync(&np, ncap, st) : cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (p) { if (st) cudaFreeAsync(p, st); else cudaFree(p); }
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return (T*)p; }
 };
@@ -90,6 +105,16 @@ struct PinBuf {
         p = nullptr;
         cap = 0;
         size_t ncap = bytes + bytes / 2 + 256;
+        cudaError_t e = cudaMallocHost(&p, ncap);
+        if (e == cudaSuccess) cap = ncap;
+        return e;
+    }
+    cudaError_t reserve_exact(size_t ncap) {
+        if (ncap <= cap) return cudaSuccess;
+        AllocScope as_("pinned(lane, presize)", ncap);
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
         cudaError_t e = cudaMallocHost(&p, ncap);
         if (e == cudaSuccess) cap = ncap;
         return e;
@@ -160,6 +185,7 @@ struct Result {
     int status;
     std::vector<uint32_t> seg_len;
     std::vector<uint8_t> seq;
+    std::string msg;  // why status != HB_OK
 };
 
 struct LastLaunch {  // host copies of per-window metadata of the most recent launch (debug taps / replay)
@@ -197,7 +223,7 @@ struct hb_ctx {
     struct ThreadSlot { std::thread::id owner; HostBatch batch; };
     std::vector<std::unique_ptr<ThreadSlot>> slots;
     PinBuf pin_in;  // staging of hb_upload_reads
-    // Two launch lanes (stream + device scratch + pinned result buffers each), one worker thread per lane:
+    // Launch lanes (stream + device scratch + pinned result buffers each), one worker thread per lane:
     // while lane A's worker does its host work (copy-back, per-read reassembly), lane B's batch keeps the GPU busy.
     struct Lane {
         cudaStream_t stream = nullptr;
@@ -208,24 +234,23 @@ struct hb_ctx {
         DevBuf d_op_kl, d_op_t, d_op_q, d_ow_nops, d_ow_flags, d_ow_acc, d_ow_tend, d_col_ow, d_w_n1, d_w_S;
         DevBuf d_ovl_n, d_ovl_tot, d_ovl_score, d_sel_ow, d_w_nsel, d_rowmap, d_w_L, d_w_rowbase, d_w_nsup, d_w_reflmax;
         DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
-        DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info;
+        DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info, d_big_key, d_big_cand, d_big_score;
         uint64_t rows_cap = 0;
+        uint64_t seen_sizes = 0;  // version of hb_ctx::lane_sizes this lane has been pre-sized to
         LastLaunch last;
         std::thread worker;
-        void bind_stream() {
-            DevBuf* bufs[] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
-                              &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
-                              &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
-                              &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
-                              &d_counters, &d_ws, &d_logits, &d_info};
-            for (DevBuf* b : bufs) b->st = stream;
+        static constexpr int N_DEV = 44;
+        void all_bufs(DevBuf* (&out)[N_DEV]) {
+            DevBuf* bufs[N_DEV] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
+                                   &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
+                                   &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
+                                   &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
+                                   &d_counters, &d_ws, &d_logits, &d_info, &d_big_key, &d_big_cand, &d_big_score};
+            for (int i = 0; i < N_DEV; i++) out[i] = bufs[i];
         }
+        void bind_stream() { DevBuf* bufs[N_DEV]; all_bufs(bufs); for (DevBuf* b : bufs) b->st = stream; }
         void release() {
-            DevBuf* bufs[] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
-                              &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
-                              &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
-                              &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
-                              &d_counters, &d_ws, &d_logits, &d_info};
+            DevBuf* bufs[N_DEV]; all_bufs(bufs);
             for (DevBuf* b : bufs) b->release();
             pin_small.release(); pin_out.release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -233,6 +258,12 @@ struct hb_ctx {
             if (stream) cudaStreamDestroy(stream);
         }
     };
+    // Largest buffer capacities any lane has needed so far.  A lane that has not run yet (or ran smaller batches) grows its
+    // buffers to these while it is idle, so that its first real batch allocates nothing (r01: 26 allocations / 226 ms inside the
+    // timed region at 8 GPUs, when host contention made the third lane start its first batch there).
+    struct LaneSizes { size_t dev[Lane::N_DEV] = {0}; size_t pin_small = 0, pin_out = 0; uint64_t rows_cap = 0; };
+    LaneSizes lane_sizes;
+    uint64_t lane_sizes_version = 0;
     static constexpr int MAX_LANES = 4;
     Lane lanes[MAX_LANES];
     int n_lanes = 3;     // HERRO_B200_LANES overrides (1..4)
@@ -257,6 +288,17 @@ struct hb_ctx {
     std::atomic<bool> time_kernels{false};  // hb_set_kernel_timing
     uint64_t alloc_base[3] = {0, 0, 0};     // g_allocs / g_alloc_ns / g_submit_wait_ns at the last hb_reset_stats
     uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
+    // debugging aids read from the environment once, in hb_create
+    bool pileup_v1 = false;          // HERRO_B200_PILEUP_V1: the former position-walk pileup kernel (A-B parity test)
+    uint32_t arena_rows_per_win = 0; // HERRO_B200_ARENA_ROWS: initial row-arena rows per window (default 1.5 W); tests shrink it
+                                     // to force the overflow -> regrow -> relaunch path
+    // staging-batch pool: every HostBatch that exists is counted, so the steady state allocates nothing
+    uint32_t batches_alive = 0;
+    // CPUs of the NUMA node the GPU hangs off (empty: unknown); launch workers are bound to them, hb_bind_calling_thread
+    // does the same for the host's feature / consumer threads
+    cpu_set_t node_cpus;
+    bool have_node_cpus = false;
+    int numa_node = -1;
 };
 
 namespace {
@@ -291,12 +333,52 @@ struct BlobEntry {
 };
 #pragma pack(pop)
 
+// NUMA node of the GPU (sysfs) and that node's CPU list: ranks sharing a box must not pile their host threads onto one socket
+void probe_numa(hb_ctx* ctx) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, ctx->device) != cudaSuccess) return;
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return;
+    path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    f = fopen(path.c_str(), "r");
+    if (!f) return;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return;
+    cpu_set_t allowed, set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+    int n = 0;
+    for (const char* p = line; *p;) {  // "0-31,64-95"
+        char* e;
+        long a = strtol(p, &e, 10), b2 = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b2 = strtol(p, &e, 10); }
+        for (long c = a; c <= b2 && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET((int)c, &allowed)) { CPU_SET((int)c, &set); n++; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    if (n == 0) return;
+    ctx->node_cpus = set;
+    ctx->have_node_cpus = true;
+    ctx->numa_node = node;
+}
+
 int load_weights(hb_ctx* ctx, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(ctx, HB_ERR_MODEL, std::string("cannot open model file ") + path);
     fseek(f, 0, SEEK_END);
     long sz = ftell(f);
     fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); return fail(ctx, HB_ERR_MODEL, "cannot size model file"); }
     std::vector<uint8_t> buf((size_t)sz);
     if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(ctx, HB_ERR_MODEL, "short read on model file"); }
     fclose(f);
@@ -319,7 +401,8 @@ int load_weights(hb_ctx* ctx, const char* path) {
         size_t eo = sizeof(BlobHeader) + (size_t)i * sizeof(BlobEntry);
         if (eo + sizeof e > (size_t)sz) return fail(ctx, HB_ERR_MODEL, "truncated tensor table");
         memcpy(&e, buf.data() + eo, sizeof e);
-        if (e.dtype != 0 || e.offset + e.nbytes > (uint64_t)sz) return fail(ctx, HB_ERR_MODEL, "bad tensor entry");
+        if (e.dtype != 0 || e.offset > (uint64_t)sz || e.nbytes > (uint64_t)sz - e.offset || (e.offset & 3u))
+            return fail(ctx, HB_ERR_MODEL, "bad tensor entry");
         char nm[49];
         memcpy(nm, e.name, 48);
         nm[48] = 0;
@@ -448,6 +531,9 @@ int ensure_batch_buffers(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     CK(L->d_ow_acc.ensure(ow1 * 4));
     CK(L->d_ow_tend.ensure(ow1 * 4));
     CK(L->d_col_ow.ensure(ow1 * 4));
+    CK(L->d_big_key.ensure(ow1 * 4));
+    CK(L->d_big_cand.ensure(ow1 * 4));
+    CK(L->d_big_score.ensure(ow1 * 8));
     CK(L->d_w_n1.ensure(nw * 4));
     CK(L->d_w_S.ensure(nw * 4));
     const size_t no1 = std::max<size_t>(no, 1);
@@ -503,6 +589,9 @@ BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     b.ow_acc = L->d_ow_acc.as<float>();
     b.ow_tend = L->d_ow_tend.as<uint32_t>();
     b.col_ow = L->d_col_ow.as<uint32_t>();
+    b.big_key = L->d_big_key.as<float>();
+    b.big_cand = L->d_big_cand.as<uint32_t>();
+    b.big_score = L->d_big_score.as<double>();
     b.w_n1 = L->d_w_n1.as<uint32_t>();
     b.w_S = L->d_w_S.as<uint32_t>();
     b.ovl_n = L->d_ovl_n.as<uint32_t>();
@@ -578,7 +667,11 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         if (sz[i]) CK(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyHostToDevice, L->stream));
     S.h2d_bytes += sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
 
-    if (L->rows_cap == 0) { rc = ensure_row_buffers(ctx, L, (uint64_t)nw * (W + W / 2) + 4096); if (rc) return rc; }
+    if (L->rows_cap == 0) {
+        const uint64_t per_win = ctx->arena_rows_per_win ? ctx->arena_rows_per_win : (uint64_t)W + W / 2;
+        rc = ensure_row_buffers(ctx, L, (uint64_t)nw * per_win + 64);
+        if (rc) return rc;
+    }
     CK(L->pin_small.ensure(CNT_N * 4 + nw * 4 * 4 + nt * 4 + nw * TOP_K * 4 + 1024));
     uint32_t* h_cnt = L->pin_small.as<uint32_t>();
     uint64_t launches = 0;
@@ -595,7 +688,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         CK(cudaEventRecord(L->ev[0], L->stream));
         launches += launch_features_a(b, L->stream, L->kt);
         CK(cudaEventRecord(L->ev[1], L->stream));
-        launches += launch_pileup(b, L->stream, L->kt);
+        launches += launch_pileup(b, L->stream, L->kt, ctx->pileup_v1);
         CK(cudaEventRecord(L->ev[2], L->stream));
         launches += launch_features_c1(b, L->stream, L->kt);  // ref_lmax + scan; the work list needs its buffers first
         CK(cudaMemcpyAsync(h_cnt, b.counters, CNT_N * 4, cudaMemcpyDeviceToHost, L->stream));
@@ -668,7 +761,14 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         const DevTarget& tg = hbt.tgt[t];
         Result r;
         r.rid = tg.rid;
-        r.status = h_terr[t] ? HB_ERR_INPUT : HB_OK;
+        r.status = HB_OK;
+        if (h_terr[t] & TERR_BAD_INPUT) {
+            r.status = HB_ERR_INPUT;
+            r.msg = "input the reference would panic on (malformed CIGAR / window descriptor / query coordinates)";
+        } else if (h_terr[t] & TERR_TOO_MANY_COLS) {
+            r.status = HB_ERR_CAPACITY;
+            r.msg = "more than " + std::to_string(MAX_COLS_HARD) + " overlap-windows in one window";
+        }
         std::vector<uint8_t> cur;
         for (uint32_t w = tg.win_begin; w < tg.win_end; w++) {
             const uint32_t len = h_outlen[w];
@@ -757,6 +857,7 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) 
     // allocated once per batch object and then recycled.  (No extrapolation from partial batches: a two-target
     // remainder scaled to a full launch once produced hints several times too large, and every pooled batch was then
     // re-pinned inside the next run.)
+    const bool first = ctx->cap_hint[0] == 0;
     {
         size_t* h = ctx->cap_hint;
         const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
@@ -771,6 +872,26 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) 
     ctx->queue.push_back(std::move(b));
     b = HostBatch(ctx->device);
     ctx->cv_work.notify_one();
+    if (first) {
+        // The first hand-over fixes the batch geometry: create the rest of the pool now (lanes in flight + queue + one per
+        // submitting thread), so that no staging batch is ever pinned in the steady state whatever the timing of the lanes.
+        const uint32_t want = (uint32_t)ctx->n_lanes + 2u + std::max<uint32_t>(ctx->n_slots.load(), 4u);
+        size_t h[5];
+        for (int i = 0; i < 5; i++) h[i] = ctx->cap_hint[i];
+        const uint32_t have = ctx->batches_alive;
+        if (want > have) {
+            ctx->batches_alive = want;
+            lk.unlock();
+            std::vector<HostBatch> fresh;
+            for (uint32_t i = have; i < want; i++) {
+                fresh.emplace_back(ctx->device);
+                HostBatch& nb = fresh.back();
+                nb.tgt.reserve(h[0]); nb.win.reserve(h[1]); nb.ovl.reserve(h[2]); nb.ow.reserve(h[3]); nb.cig.reserve(h[4]);
+            }
+            lk.lock();
+            for (auto& nb : fresh) ctx->pool.push_back(std::move(nb));
+        }
+    }
 }
 
 // A staging batch with capacity: recycled from the pool, else allocated once at the largest size seen so far
@@ -780,7 +901,7 @@ void acquire_batch(hb_ctx* ctx, HostBatch& b) {
     size_t h[5];
     for (int i = 0; i < 5; i++) h[i] = ctx->cap_hint[i];
     if (!ctx->pool.empty()) { b = std::move(ctx->pool.back()); ctx->pool.pop_back(); }
-    else b = HostBatch(ctx->device);
+    else { b = HostBatch(ctx->device); ctx->batches_alive++; }
     lk.unlock();
     if (h[0]) { b.tgt.reserve(h[0]); b.win.reserve(h[1]); b.ovl.reserve(h[2]); b.ow.reserve(h[3]); b.cig.reserve(h[4]); }
 }
@@ -800,15 +921,57 @@ hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
     return tl_slot;
 }
 
+// Record the capacities this lane ended up with; other lanes grow to them while idle (see hb_ctx::LaneSizes).  Lock held.
+void publish_lane_sizes(hb_ctx* ctx, hb_ctx::Lane* L) {
+    DevBuf* bufs[hb_ctx::Lane::N_DEV];
+    L->all_bufs(bufs);
+    bool grew = false;
+    hb_ctx::LaneSizes& T = ctx->lane_sizes;
+    for (int i = 0; i < hb_ctx::Lane::N_DEV; i++)
+        if (bufs[i]->cap > T.dev[i]) { T.dev[i] = bufs[i]->cap; grew = true; }
+    if (L->pin_small.cap > T.pin_small) { T.pin_small = L->pin_small.cap; grew = true; }
+    if (L->pin_out.cap > T.pin_out) { T.pin_out = L->pin_out.cap; grew = true; }
+    if (L->rows_cap > T.rows_cap) { T.rows_cap = L->rows_cap; grew = true; }
+    if (grew) ctx->lane_sizes_version++;
+    bool below = L->pin_small.cap < T.pin_small || L->pin_out.cap < T.pin_out || L->rows_cap < T.rows_cap;
+    for (int i = 0; i < hb_ctx::Lane::N_DEV; i++) below = below || bufs[i]->cap < T.dev[i];
+    if (!below) L->seen_sizes = ctx->lane_sizes_version;  // else: this lane catches up when it is next idle
+}
+
+// Grow an idle lane's buffers to the recorded sizes (no lock held; only this lane's worker touches its buffers).
+void presize_lane(hb_ctx::Lane* L, const hb_ctx::LaneSizes& T) {
+    DevBuf* bufs[hb_ctx::Lane::N_DEV];
+    L->all_bufs(bufs);
+    bool ok = true;
+    for (int i = 0; i < hb_ctx::Lane::N_DEV; i++) ok = ok && bufs[i]->reserve_exact(T.dev[i]) == cudaSuccess;
+    ok = ok && L->pin_small.reserve_exact(T.pin_small) == cudaSuccess && L->pin_out.reserve_exact(T.pin_out) == cudaSuccess;
+    if (ok && T.rows_cap > L->rows_cap) L->rows_cap = T.rows_cap;  // the six row-sized buffers are part of dev[]
+    cudaStreamSynchronize(L->stream);
+}
+
 void worker_main(hb_ctx* ctx, int lane) {
     cudaSetDevice(ctx->device);
+    if (ctx->have_node_cpus) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), &ctx->node_cpus);
     hb_ctx::Lane* L = &ctx->lanes[lane];
     std::string my_err;
     t_err_sink = &my_err;
     std::unique_lock<std::mutex> lk(ctx->mu);
     for (;;) {
-        ctx->cv_work.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
-        if (ctx->queue.empty()) break;  // stop requested and nothing left
+        ctx->cv_work.wait(lk, [&] { return ctx->stop || !ctx->queue.empty() || L->seen_sizes != ctx->lane_sizes_version; });
+        if (ctx->queue.empty()) {
+            if (ctx->stop) break;  // stop requested and nothing left
+            // idle and another lane has grown: pre-size this lane now rather than inside its next launch
+            const hb_ctx::LaneSizes T = ctx->lane_sizes;
+            const uint64_t ver = ctx->lane_sizes_version;
+            ctx->busy++;  // hb_flush / replay must not run while buffers move
+            lk.unlock();
+            presize_lane(L, T);
+            lk.lock();
+            L->seen_sizes = ver;
+            ctx->busy--;
+            ctx->cv_idle.notify_all();
+            continue;
+        }
         HostBatch hbt = std::move(ctx->queue.front());
         ctx->queue.pop_front();
         ctx->busy++;
@@ -818,7 +981,11 @@ void worker_main(hb_ctx* ctx, int lane) {
         lk.lock();
         if (rc != HB_OK) {
             if (ctx->worker_rc == HB_OK) { ctx->worker_rc = rc; ctx->worker_err = my_err; }
-            for (const auto& t : hbt.tgt) ctx->results.push_back(Result{t.rid, rc, {}, {}});
+            for (const auto& t : hbt.tgt) ctx->results.push_back(Result{t.rid, rc, {}, {}, "launch failed: " + my_err});
+        } else {
+            const uint64_t before = ctx->lane_sizes_version;
+            publish_lane_sizes(ctx, L);
+            if (ctx->lane_sizes_version != before) ctx->cv_work.notify_all();
         }
         hbt.clear();
         ctx->pool.push_back(std::move(hbt));
@@ -941,6 +1108,13 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (cudaSetDevice(cuda_device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(HB_ERR_CUDA); }
     if (const char* e = getenv("HERRO_B200_CHUNK_POS")) ctx->chunk_pos = (uint32_t)std::min(std::max(atoi(e), 128), 65536);
     if (const char* e = getenv("HERRO_B200_LANES")) ctx->n_lanes = std::min(std::max(atoi(e), 1), (int)hb_ctx::MAX_LANES);
+    // debugging aids / A-B parity tests: read here once, never on the launch path
+    ctx->pileup_v1 = getenv("HERRO_B200_PILEUP_V1") != nullptr;
+    if (const char* e = getenv("HERRO_B200_ARENA_ROWS")) ctx->arena_rows_per_win = (uint32_t)std::max(atoi(e), 1);
+    ctx->wt.no_fuse_ln = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;
+    ctx->wt.no_fuse_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;
+    ctx->wt.no_fuse_attn = getenv("HERRO_B200_NO_FUSE_ATTN") != nullptr;
+    if (!getenv("HERRO_B200_NO_NUMA_BIND")) probe_numa(ctx);
     for (int li = 0; li < ctx->n_lanes; li++) {
         auto& L = ctx->lanes[li];
         if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(HB_ERR_CUDA); }
@@ -1001,9 +1175,15 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
         max_len = std::max(max_len, seq_len[i]);
         if (!seq_words[i] || !qual[i]) return fail(ctx, HB_ERR_ARG, "null read");
     }
-    CK(ctx->d_words.ensure((woff[n_reads] + 8) * 8));  // padded: packed 32-base extraction may touch a few words past a read
-    CK(cudaMemset(ctx->d_words.as<uint64_t>() + woff[n_reads], 0, 8 * 8));
-    CK(ctx->d_qual.ensure(qoff[n_reads] + 16));
+    // Padded on both sides: packed 32-base extraction may touch a few words past a read, and the pileup kernel fetches the
+    // 4 bases / 4 quality bytes of a row group as whole words that may start up to 7 bytes before a read (pileup.cu).
+    constexpr size_t FRONT_WORDS = 32, FRONT_QUAL = 256;  // keeps both bases 256-byte aligned
+    CK(ctx->d_words.ensure((FRONT_WORDS + woff[n_reads] + 8) * 8));
+    CK(cudaMemset(ctx->d_words.p, 0, FRONT_WORDS * 8));
+    CK(cudaMemset(ctx->d_words.as<uint64_t>() + FRONT_WORDS + woff[n_reads], 0, 8 * 8));
+    CK(ctx->d_qual.ensure(FRONT_QUAL + qoff[n_reads] + 16));
+    CK(cudaMemset(ctx->d_qual.p, 33, FRONT_QUAL));
+    CK(cudaMemset(ctx->d_qual.as<uint8_t>() + FRONT_QUAL + qoff[n_reads], 33, 16));
     CK(ctx->d_word_off.ensure((n_reads + 1) * 8));
     CK(ctx->d_qual_off.ensure((n_reads + 1) * 8));
     CK(ctx->d_len.ensure((size_t)n_reads * 4));
@@ -1030,10 +1210,10 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
         return HB_OK;
     };
     int rc = copy_stream([&](uint32_t i) { return (const void*)seq_words[i]; },
-                         [&](uint32_t i) { return (size_t)(((uint64_t)seq_len[i] + 31) / 32 * 8); }, ctx->d_words.as<uint8_t>());
+                         [&](uint32_t i) { return (size_t)(((uint64_t)seq_len[i] + 31) / 32 * 8); }, ctx->d_words.as<uint8_t>() + FRONT_WORDS * 8);
     if (rc) return rc;
     rc = copy_stream([&](uint32_t i) { return (const void*)qual[i]; }, [&](uint32_t i) { return (size_t)seq_len[i]; },
-                     ctx->d_qual.as<uint8_t>());
+                     ctx->d_qual.as<uint8_t>() + FRONT_QUAL);
     if (rc) return rc;
     CK(cudaMemcpy(ctx->d_word_off.p, woff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_qual_off.p, qoff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice));
@@ -1048,8 +1228,8 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
     ctx->stats.h2d_bytes += woff[n_reads] * 8 + qoff[n_reads];
     ctx->n_reads = n_reads;
     ctx->read_len.assign(seq_len, seq_len + n_reads);
-    ctx->rs = ReadStoreView{ctx->d_words.as<uint64_t>(), ctx->d_word_off.as<uint64_t>(), ctx->d_len.as<uint32_t>(),
-                            ctx->d_qual.as<uint8_t>(), ctx->d_qual_off.as<uint64_t>(), n_reads};
+    ctx->rs = ReadStoreView{ctx->d_words.as<uint64_t>() + FRONT_WORDS, ctx->d_word_off.as<uint64_t>(), ctx->d_len.as<uint32_t>(),
+                            ctx->d_qual.as<uint8_t>() + FRONT_QUAL, ctx->d_qual_off.as<uint64_t>(), n_reads};
     ctx->have_reads = true;
     return HB_OK;
 }
@@ -1151,6 +1331,15 @@ int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg
         r = std::move(ctx->results.front());
         ctx->results.pop_front();
     }
+    *rid = r.rid;
+    *seqs = nullptr;
+    *seg_len = nullptr;
+    *n_segs = 0;
+    if (r.status != HB_OK) {  // nothing is allocated for a failed target: there is nothing to release
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->err = "target " + std::to_string(r.rid) + ": " + r.msg;
+        return r.status;
+    }
     const size_t ns = r.seg_len.size();
     const size_t hdr = ((ns * 4 + 15) & ~(size_t)15) + 16;
     uint8_t* blk = (uint8_t*)malloc(hdr + r.seq.size() + 16);
@@ -1159,16 +1348,16 @@ int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg
     const uint64_t tag[2] = {(uint64_t)hdr, RESULT_MAGIC};
     memcpy(blk + hdr - 16, tag, 16);
     memcpy(blk + hdr, r.seq.data(), r.seq.size());
-    *rid = r.rid;
     *seg_len = (uint32_t*)blk;
     *seqs = blk + hdr;
     *n_segs = (uint32_t)ns;
-    if (r.status != HB_OK) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        ctx->err = "target " + std::to_string(r.rid) + ": input the reference would panic on (malformed CIGAR / window)";
-        return r.status;
-    }
     return 1;
+}
+
+int hb_bind_calling_thread(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->have_node_cpus) return 0;
+    return pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), &ctx->node_cpus) == 0 ? 1 : 0;
 }
 
 void hb_release_result(hb_ctx* ctx, uint8_t* seqs) {
@@ -1362,7 +1551,7 @@ int hb_replay_last_launch(hb_ctx* ctx, uint32_t iters, float* ms) {
         int rc = zero_scratch(ctx, L, b);
         if (rc) return rc;
         launches += launch_features_a(b, L->stream, L->kt);
-        launches += launch_pileup(b, L->stream, L->kt);
+        launches += launch_pileup(b, L->stream, L->kt, ctx->pileup_v1);
         launches += launch_features_c1(b, L->stream, L->kt);
         rc = launch_tail(ctx, L, b, L->last.n_sup, &launches);
         if (rc) return rc;

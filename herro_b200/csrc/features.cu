@@ -202,11 +202,15 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
     const uint32_t n_in = win.ow_end - win.ow_begin;
     if (tid == 0) { s_n1 = 0; s_S = 0; s_carry = 0; }
     __syncthreads();
-    if (n_in > MAX_COLS) {
+    if (n_in > MAX_COLS_HARD) {  // the per-position counters are 16 bits wide
         if (tid == 0) { atomicOr(&b.tgt_err[win.tgt], TERR_TOO_MANY_COLS); b.w_n1[w] = 0; b.w_S[w] = 0; }
         return;
     }
-    // ---- filter (order preserving compaction; n_in <= MAX_COLS so <= 4 rounds)
+    if (n_in > MAX_COLS) {  // the reference has no limit (src/features.rs:376-418): the sort keys of a huge window live in HBM
+        key = b.big_key + win.ow_begin;
+        cand = b.big_cand + win.ow_begin;
+    }
+    // ---- filter (order preserving compaction)
     for (uint32_t base = 0; base < n_in; base += 256) {
         const uint32_t i = base + tid;
         const bool keep = i < n_in && !(b.ow_flags[win.ow_begin + i] & (OWF_LONG_INDEL | OWF_BAD));
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(256) k_pass2a(BatchView b) {
     const uint32_t W = b.W;
     uint32_t* mi = (uint32_t*)smem_raw;            // W + 1
     double* sc = (double*)(mi + ((W + 2) & ~1u));   // MAX_COLS
+    if (b.win[blockIdx.x].ow_end - b.win[blockIdx.x].ow_begin > MAX_COLS) sc = b.big_score + b.win[blockIdx.x].ow_begin;
     __shared__ uint32_t s_sel[TOP_K], s_warp[8], s_carry;
 
     const uint32_t w = blockIdx.x;
@@ -876,7 +881,9 @@ cudaError_t features_configure(uint32_t W) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_pass2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2a_smem(W));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_pass2b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2b_smem());
+    e = cudaFuncSetAttribute(k_pass2b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2b_smem());
+    if (e != cudaSuccess) return e;
+    return pileup_configure();
 }
 
 int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
@@ -890,8 +897,11 @@ int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
     kt.end(); n++;
     return n;
 }
-int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt) {
-    kt.begin(K_PILEUP); k_pass2b<<<b.n_win, 256, pass2b_smem(), st>>>(b); kt.end();
+int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt, bool v1) {
+    kt.begin(K_PILEUP);
+    if (v1) k_pass2b<<<b.n_win, 256, pass2b_smem(), st>>>(b);  // former position-walk kernel (A-B parity test only)
+    else launch_pileup_v2(b, st);
+    kt.end();
     return 1;
 }
 int launch_features_c1(const BatchView& b, cudaStream_t st, KTimer& kt) {

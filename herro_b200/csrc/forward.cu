@@ -324,9 +324,7 @@ struct FwdWs {
     __nv_bfloat16 *Hhi, *Hlo, *Fhi, *Flo;
     size_t bytes;
 };
-static bool ffn_is_fused(const FwdWeights& wt) {  // the environment is read per call: the A-B parity tests toggle it
-    return wt.C == 128 && wt.F == 512 && getenv("HERRO_B200_NO_FUSE_LN") == nullptr && getenv("HERRO_B200_NO_FUSE_FFN") == nullptr;
-}
+static bool ffn_is_fused(const FwdWeights& wt) { return wt.C == 128 && wt.F == 512 && !wt.no_fuse_ln && !wt.no_fuse_ffn; }
 static FwdWs carve(const FwdWeights& wt, size_t npos, uint8_t* base) {
     const size_t np = (npos + 127) / 128 * 128;  // positions padded to a GEMM tile
     const size_t T = np * TOK_PER_POS;
@@ -397,7 +395,7 @@ uint64_t forward_flops_per_pos(const FwdWeights& wt, uint64_t* gemm_flops) {
     return stem + g + (uint64_t)wt.layers * per_layer_attn + heads;
 }
 
-static bool attn_is_fused(const FwdWeights& wt) { return wt.layer[0].bqkvp && getenv("HERRO_B200_NO_FUSE_ATTN") == nullptr; }
+static bool attn_is_fused(const FwdWeights& wt) { return wt.layer[0].bqkvp && !wt.no_fuse_attn; }
 void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]) {
     const uint64_t C = wt.C, F = wt.F, D = wt.D, K = wt.stem_k, S = R_COLS, dh = wt.C / wt.H, L = wt.layers;
     for (auto& o : out) o = 0;
@@ -425,7 +423,7 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
     const unsigned ln_blocks = (unsigned)((T * 32 + 255) / 256);
     // With C == 128 a kernel that writes the residual stream owns whole rows in its epilogue, so the LayerNorm that
     // follows is computed there (stem epilogue, GEMM_OUT_F32_RES_LN, fused FFN); k_layernorm is the fallback.
-    const bool no_fuse = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;  // debugging aid / A-B parity test
+    const bool no_fuse = wt.no_fuse_ln != 0;  // debugging aid / A-B parity test
     const bool fuse_ln = (C == 128) && !no_fuse;
     const bool stem_ln = fuse_ln && wt.stem_kblocks;
     if (stem_ln && T > (size_t)npos * TOK_PER_POS) {  // rows of the pad positions: defined operands for the contractions

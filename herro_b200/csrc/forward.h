@@ -34,6 +34,8 @@ struct FwdWeights {
     SplitW s_stem;          // W' of the tensor-core stem, [C][stem_kp]
     int stem_kblocks = 0;   // 0: tensor-core stem unavailable (C != 128 or too many taps)
     int num_sms;
+    // debugging aids / A-B parity tests, read from the environment ONCE in hb_create (HERRO_B200_NO_FUSE_{LN,FFN,ATTN})
+    int no_fuse_ln = 0, no_fuse_ffn = 0, no_fuse_attn = 0;
 };
 
 // gemm_tc.cu
@@ -137,7 +139,10 @@ void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]);
 // features.cu
 cudaError_t features_configure(uint32_t W);
 int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt);
-int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt);
+int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt, bool v1);
+// pileup.cu
+cudaError_t pileup_configure();
+void launch_pileup_v2(const BatchView& b, cudaStream_t st);
 int launch_features_c1(const BatchView& b, cudaStream_t st, KTimer& kt);
 int launch_features_c2(const BatchView& b, cudaStream_t st, KTimer& kt);
 int launch_consensus(const BatchView& b, cudaStream_t st, KTimer& kt);

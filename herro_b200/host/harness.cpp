@@ -57,8 +57,9 @@ int hbh_windowing(const hb_overlap* ovl_all, const uint64_t* aln_off, const uint
 }
 
 // Run targets [t_begin, t_end).  ow_all/ow_off: precomputed windows (hbh_windowing) or NULL to let the
-// library window the alignments (hb_submit_alignments).  out3 = {corrected bases, records (segments),
-// targets that produced output}; checksum = order-independent hash of (rid, segment bytes).
+// library window the alignments (hb_submit_alignments).  out4 = {corrected bases, records (segments),
+// targets that produced output, targets that failed (skipped, the run goes on)}; checksum = order-independent
+// hash of (rid, segment bytes).  Every thread binds itself to the NUMA node of the context's GPU.
 int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, const uint32_t* read_len, uint32_t window,
             uint32_t t_begin, uint32_t t_end, int threads, const hb_overlap_window* ow_all, const uint64_t* ow_off,
             uint64_t* out3, uint64_t* checksum, double* seconds, double* submit_seconds_sum) {
@@ -68,7 +69,9 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
     std::atomic<int> producers_left{threads > 0 ? threads : 1};
     const auto t0 = std::chrono::steady_clock::now();
     std::atomic<uint64_t> submit_ns{0};
+    std::atomic<uint64_t> failed{0};
     auto feature_thread = [&]() {
+        hb_bind_calling_thread(ctx);
         uint64_t my_ns = 0;
         for (;;) {
             const uint32_t t = next.fetch_add(1);
@@ -92,6 +95,7 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
     };
     uint64_t bases = 0, records = 0, targets = 0, sum = 0;
     auto consumer = [&]() {
+        hb_bind_calling_thread(ctx);
         bool flushed = false;
         for (;;) {
             uint32_t rid = 0, n = 0;
@@ -115,14 +119,16 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
                 if (producers_left.load() == 0) {
                     if (flushed) break;
                     const int f = hb_flush(ctx);
-                    if (f != 0) rc = f;
+                    if (f != 0 && f != HB_ERR_INPUT && f != HB_ERR_CAPACITY) rc = f;
                     flushed = true;
                 } else {
                     std::this_thread::sleep_for(std::chrono::microseconds(100));
                 }
+            } else if (r == HB_ERR_INPUT || r == HB_ERR_CAPACITY) {
+                failed.fetch_add(1);  // this target only: log-and-continue (hb_last_error names it)
             } else {
-                if (seqs) hb_release_result(ctx, seqs);
                 rc = r;
+                if (flushed) break;
             }
         }
     };
@@ -132,7 +138,7 @@ int hbh_run(hb_ctx* ctx, const hb_overlap* ovl_all, const uint64_t* aln_off, con
     for (auto& t : th) t.join();
     cons.join();
     *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    out3[0] = bases; out3[1] = records; out3[2] = targets;
+    out3[0] = bases; out3[1] = records; out3[2] = targets; out3[3] = failed.load();
     if (checksum) *checksum = sum;
     if (submit_seconds_sum) *submit_seconds_sum = (double)submit_ns.load() * 1e-9;
     return rc;

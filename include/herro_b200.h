@@ -37,7 +37,8 @@ typedef enum hb_status {
     HB_ERR_CUDA = -2,     /* CUDA runtime failure (no device, OOM, launch error)                */
     HB_ERR_MODEL = -3,    /* weights file missing / malformed / unsupported dimensions          */
     HB_ERR_INPUT = -4,    /* input on which the reference itself would panic (bad CIGAR, ...)   */
-    HB_ERR_CAPACITY = -5, /* an internal capacity was exceeded and could not be grown           */
+    HB_ERR_CAPACITY = -5, /* an internal capacity was exceeded and could not be grown (e.g. more   */
+                          /* than 60000 overlaps covering one window, out of memory)            */
     HB_ERR_STATE = -6     /* call sequence error (e.g. submit before hb_upload_reads)           */
 } hb_status;
 
@@ -127,7 +128,11 @@ int hb_set_kernel_timing(hb_ctx* ctx, int on);
 int hb_flush(hb_ctx* ctx);
 
 /* Pop one finished target: the `(rid, Vec<Vec<u8>>)` of src/consensus.rs:253-257.
- * Returns 1 and fills the outputs if a result was popped, 0 if none is queued, <0 on error.
+ * Returns 1 and fills the outputs if a result was popped, 0 if none is queued, <0 if the popped target
+ * failed: then *rid names it, *seqs / *seg_len are NULL, *n_segs is 0 (nothing to release), hb_last_error()
+ * says why (HB_ERR_INPUT: the reference would have panicked on its alignments; HB_ERR_CAPACITY / HB_ERR_CUDA:
+ * its launch failed), and the other targets are unaffected — a host that wants the reference's behaviour
+ * aborts, one that wants to keep going logs the read and polls on.
  * `*seqs` = the segments back to back (ASCII ACGT), `*seg_len[k]` their lengths; n_segs == 0
  * means consensus() returned None or produced nothing — the read is omitted from the FASTA
  * (src/consensus.rs:95-98, src/lib.rs:282-288).  Buffers stay valid until
@@ -136,6 +141,11 @@ int hb_poll_corrected(hb_ctx* ctx, uint32_t* rid, uint8_t** seqs, uint32_t** seg
 void hb_release_result(hb_ctx* ctx, uint8_t* seqs);
 
 const char* hb_last_error(hb_ctx* ctx); /* ctx may be NULL: error of a failed hb_create */
+
+/* Bind the calling thread to the CPUs of the NUMA node the context's GPU is attached to (the library's own
+ * launch workers always are).  For the host's feature / consumer threads of this device (src/lib.rs:159-199) on
+ * multi-socket boxes.  Returns 1 if bound, 0 if the topology is unknown (nothing changed), <0 on error. */
+int hb_bind_calling_thread(hb_ctx* ctx);
 
 /* ---- counters (the reference only has progress bars, src/pbars.rs) -------------------- */
 #define HB_NUM_KERNEL_CLASSES 16

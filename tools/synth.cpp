@@ -109,7 +109,10 @@ struct synth_set;  // opaque = Set
 
 void* synth_generate(uint64_t seed, uint64_t genome_len, uint32_t n_reads, uint32_t mean_len, uint32_t sd_len,
                      uint32_t min_len, uint32_t max_len, double sub, double ins, double del, double hp_boost,
-                     double het_snp, double het_indel, double long_del, uint32_t min_ovl, uint32_t n_threads) {
+                     double het_snp, double het_indel, double long_del, uint32_t min_ovl, uint32_t n_threads,
+                     uint32_t tgt_begin, uint32_t tgt_end, uint32_t tgt_stride, uint32_t tgt_phase) {
+    // alignments are produced only for targets t in [tgt_begin, tgt_end) with t % tgt_stride == tgt_phase (every read is still
+    // generated: queries come from the whole set) — a rank of a sharded run builds just its own targets' alignments
     Set* S = new Set();
     S->p = Params{seed, genome_len, n_reads, mean_len, sd_len, min_len, max_len, sub, ins, del,
                   hp_boost, het_snp, het_indel, long_del, min_ovl};
@@ -267,6 +270,7 @@ void* synth_generate(uint64_t seed, uint64_t genome_len, uint32_t n_reads, uint3
                 const Read& T = S->reads[t];
                 PerTarget& P = per[t];
                 P.coff.push_back(0);
+                if (t < tgt_begin || t >= tgt_end || (tgt_stride > 1 && t % tgt_stride != tgt_phase)) continue;
                 // candidates: reads whose start lies in (T.gs - max_glen, T.ge)
                 int64_t k0 = (int64_t)rank[t];
                 while (k0 > 0 && S->reads[order[k0 - 1]].gs + max_glen > T.gs) k0--;

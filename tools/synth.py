@@ -64,13 +64,15 @@ class ReadSet:
 
 def generate(n_reads: int, mean_len: int, *, profile="r10", seed=1, coverage=40.0, sd_frac=0.10, min_len=None,
              max_len=None, het_snp=1e-3, het_indel=1e-4, long_del=2e-6, min_ovl=2048, genome_len=None,
-             threads=None) -> ReadSet:
+             threads=None, targets=None, target_stride=(1, 0)) -> ReadSet:
+    """targets=(begin, end) / target_stride=(stride, phase): build alignments only for those target reads (all reads are
+    always generated, so the read store and every query are those of the full set)."""
     build()
     L = C.CDLL(_LIB)
     L.synth_generate.restype = C.c_void_p
     L.synth_generate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                  C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
-                                 C.c_uint32, C.c_uint32]
+                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.synth_free.argtypes = [C.c_void_p]
     L.synth_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     vp = C.c_void_p
@@ -82,8 +84,9 @@ def generate(n_reads: int, mean_len: int, *, profile="r10", seed=1, coverage=40.
     min_len = min_len if min_len is not None else max(int(mean_len * 0.5), 1)
     max_len = max_len if max_len is not None else int(mean_len * 2)
     threads = threads or os.cpu_count() or 1
+    tb, te = targets if targets is not None else (0, n_reads)
     h = L.synth_generate(seed, genome_len, n_reads, mean_len, int(mean_len * sd_frac), min_len, max_len, sub, ins,
-                         dele, hpb, het_snp, het_indel, long_del, min_ovl, threads)
+                         dele, hpb, het_snp, het_indel, long_del, min_ovl, threads, tb, te, target_stride[0], target_stride[1])
     try:
         sz = (C.c_uint64 * 4)()
         L.synth_sizes(h, sz)
