@@ -201,8 +201,11 @@ class Context:
         woff = np.zeros(n + 1, dtype=np.uint64)
         woff[1:] = np.cumsum((lens.astype(np.uint64) + 31) // 32)
         words = np.zeros(int(woff[-1]) + 1, dtype=np.uint64)
-        for i in range(n):
-            words[int(woff[i]):int(woff[i + 1])] = pack_2bit(seqs[int(off[i]):int(off[i + 1])])
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        off64 = np.ascontiguousarray(off, dtype=np.uint64)
+        if _host_lib().hbh_pack_2bit(seqs.ctypes.data, off64.ctypes.data, n, words.ctypes.data, woff.ctypes.data,
+                                     min(os.cpu_count() or 1, 32)) != 0:
+            raise ValueError("non-ACGT base: the reference's 2-bit packing is undefined for it (SURVEY.md H12)")
         quals = np.ascontiguousarray(quals, dtype=np.uint8)
         wp = (words.ctypes.data + woff[:-1] * 8).astype(np.uint64)
         qp = (quals.ctypes.data + off[:-1].astype(np.uint64)).astype(np.uint64)
@@ -333,6 +336,7 @@ def _host_lib():
         load_library()
         H = C.CDLL(HOST_LIB_PATH)
         vp, u32 = C.c_void_p, C.c_uint32
+        H.hbh_pack_2bit.argtypes = [vp, vp, u32, vp, vp, C.c_int]
         H.hbh_windowing.argtypes = [vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, C.c_uint64]
         H.hbh_run.argtypes = [vp, vp, vp, vp, u32, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp]
         _host = H

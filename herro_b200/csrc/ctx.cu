@@ -79,13 +79,15 @@ struct DevBuf {
         cap = ncap;
         return cudaSuccess;
     }
-    // grow to exactly `ncap` bytes without headroom (pre-sizing an idle lane from another lane's sizes); contents are not kept
+    // grow to exactly `ncap` bytes without headroom (pre-sizing an idle lane from another lane's sizes); contents are kept
+    // (the lane's last launch stays replayable / inspectable through the debug taps)
     cudaError_t reserve_exact(size_t ncap) {
         if (ncap <= cap) return cudaSuccess;
         AllocScope as_(st ? "device(stream-ordered, presize)" : "device(presize)", ncap);
         void* np = nullptr;
         cudaError_t e = st ? cudaMallocAsync(&np, ncap, st) : cudaMalloc(&np, ncap);
         if (e != cudaSuccess) return e;
+        if (p && cap) { if (st) cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st); else cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice); }
         if (p) { if (st) cudaFreeAsync(p, st); else cudaFree(p); }
         p = np;
         cap = ncap;
@@ -567,15 +569,9 @@ int ensure_row_buffers(hb_ctx* ctx, hb_ctx::Lane* L, uint64_t rows) {
     return HB_OK;
 }
 
-BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
-    BatchView b{};
+// the pointer fields of a view: the lane's buffers as they are now
+void set_view_ptrs(hb_ctx* ctx, hb_ctx::Lane* L, BatchView& b) {
     b.rs = ctx->rs;
-    b.W = ctx->opt.window_size;
-    b.n_tgt = (uint32_t)hbt.tgt.size();
-    b.n_win = (uint32_t)hbt.win.size();
-    b.n_ovl = (uint32_t)hbt.ovl.size();
-    b.n_ow = (uint32_t)hbt.ow.size();
-    b.batch_size = ctx->opt.batch_size;
     b.tgt = L->d_tgt.as<DevTarget>();
     b.win = L->d_win.as<DevWin>();
     b.ovl = L->d_ovl.as<DevOverlap>();
@@ -606,7 +602,6 @@ BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     b.w_rowbase = L->d_w_rowbase.as<uint64_t>();
     b.w_nsup = L->d_w_nsup.as<uint32_t>();
     b.w_reflmax = L->d_w_reflmax.as<uint32_t>();
-    b.rows_cap = L->rows_cap;
     b.mat_bases = L->d_mat_b.as<uint8_t>();
     b.mat_quals = L->d_mat_q.as<uint8_t>();
     b.row_emit = L->d_row_emit.as<uint8_t>();
@@ -620,6 +615,18 @@ BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     b.out_bytes = L->d_out.as<uint8_t>();
     b.tgt_err = L->d_tgt_err.as<uint32_t>();
     b.counters = L->d_counters.as<uint32_t>();
+}
+
+BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
+    BatchView b{};
+    b.W = ctx->opt.window_size;
+    b.n_tgt = (uint32_t)hbt.tgt.size();
+    b.n_win = (uint32_t)hbt.win.size();
+    b.n_ovl = (uint32_t)hbt.ovl.size();
+    b.n_ow = (uint32_t)hbt.ow.size();
+    b.batch_size = ctx->opt.batch_size;
+    b.rows_cap = L->rows_cap;
+    set_view_ptrs(ctx, L, b);
     return b;
 }
 
@@ -939,7 +946,7 @@ void publish_lane_sizes(hb_ctx* ctx, hb_ctx::Lane* L) {
 }
 
 // Grow an idle lane's buffers to the recorded sizes (no lock held; only this lane's worker touches its buffers).
-void presize_lane(hb_ctx::Lane* L, const hb_ctx::LaneSizes& T) {
+void presize_lane(hb_ctx* ctx, hb_ctx::Lane* L, const hb_ctx::LaneSizes& T) {
     DevBuf* bufs[hb_ctx::Lane::N_DEV];
     L->all_bufs(bufs);
     bool ok = true;
@@ -947,7 +954,9 @@ void presize_lane(hb_ctx::Lane* L, const hb_ctx::LaneSizes& T) {
     ok = ok && L->pin_small.reserve_exact(T.pin_small) == cudaSuccess && L->pin_out.reserve_exact(T.pin_out) == cudaSuccess;
     if (ok && T.rows_cap > L->rows_cap) L->rows_cap = T.rows_cap;  // the six row-sized buffers are part of dev[]
     cudaStreamSynchronize(L->stream);
+    if (L->last.valid) set_view_ptrs(ctx, L, L->last.view);  // buffers moved (contents copied): the kept view follows them
 }
+
 
 void worker_main(hb_ctx* ctx, int lane) {
     cudaSetDevice(ctx->device);
@@ -965,7 +974,7 @@ void worker_main(hb_ctx* ctx, int lane) {
             const uint64_t ver = ctx->lane_sizes_version;
             ctx->busy++;  // hb_flush / replay must not run while buffers move
             lk.unlock();
-            presize_lane(L, T);
+            presize_lane(ctx, L, T);
             lk.lock();
             L->seen_sizes = ver;
             ctx->busy--;

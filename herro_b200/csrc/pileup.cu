@@ -47,9 +47,9 @@ struct __align__(16) ColC { uint32_t gap4, xr4, add4, rsel; };
 __device__ __constant__ uint16_t c_sel16[16] = {
     0x7654, 0x7650, 0x7604, 0x7610, 0x7054, 0x7150, 0x7104, 0x7210,
     0x0654, 0x1650, 0x1604, 0x2610, 0x1054, 0x2150, 0x2104, 0x3210};
-// class-count increments: five 5-bit counters (A C G T gap) in one word; tokens 10 ('.') and 11 (pad) count nothing
-__device__ __constant__ uint32_t c_cls[16] = {1u, 1u << 5, 1u << 10, 1u << 15, 1u << 20, 1u, 1u << 5, 1u << 10,
-                                              1u << 15, 1u << 20, 0u, 0u, 0u, 0u, 0u, 0u};
+// class-count increments: five 6-bit counters (A C G T gap; a count is <= 31, bit 5 of a field is headroom for the threshold
+// test) in one word; tokens 10 ('.') and 11 (pad) count nothing.  The table is indexed by a PAIR of tokens (t0 | t1 << 4).
+__host__ __device__ constexpr uint32_t cls_inc(uint32_t t) { return t < 10u ? 1u << (6u * (t < 5u ? t : t - 5u)) : 0u; }
 
 // toggle the two ends of the row range [a, e) clipped to the chunk [c0, c0 + P_CH)
 __device__ __forceinline__ void toggle_range(uint32_t* T, uint32_t a, uint32_t e, uint32_t c0) {
@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     ColB* colB = (ColB*)(colA + 32);
     ColC* colC = (ColC*)(colB + 32);
     uint32_t* sel_s = (uint32_t*)(colC + 32);           // [16]
-    uint32_t* cls_s = sel_s + 16;                       // [16]
+    uint32_t* cls_s = sel_s + 16;                       // [256]
     __shared__ uint32_t s_ow[32], s_x0[32], s_carry[32], s_tot[33], s_warp[8];
+    __shared__ uint32_t s_opb[32], s_opoff[33];  // op arrays of the columns: first slot, and the exclusive prefix of their op counts
     __shared__ const uint8_t* s_qp0[32];
     __shared__ uint32_t s_nsup, s_pcarry;
 
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     if (tid < 32) {
         const uint32_t c = tid;
         ColA a; ColB bb; ColC cc;
-        uint32_t owi = 0, x0 = 0;
+        uint32_t owi = 0, x0 = 0, nops_c = 0, opb_c = 0;
         const uint8_t* qp0;
         const uint64_t* words;
         bb.sgn = 0; bb.rs = 0; bb.re = 0; bb.x0 = 0;
@@ -114,6 +115,8 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
             owi = b.sel_ow[w * TOP_K + c - 1];
             const DevOW ow = b.ow[owi];
             const DevOverlap ov = b.ovl[ow.ovl];
+            nops_c = b.ow_nops[owi];
+            opb_c = ow.op_base;
             words = b.rs.words + b.rs.word_off[ov.qid];
             qp0 = b.rs.qual + b.rs.qual_off[ov.qid];
             bb.rs = rm[ow.tstart - win.tstart];  // rows before are '.' (src/features.rs:166-171)
@@ -135,8 +138,13 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
         a.qp = qp0;
         colA[c] = a; colB[c] = bb; colC[c] = cc;
         s_ow[c] = owi; s_x0[c] = x0; s_qp0[c] = qp0; s_carry[c] = 0;
+        s_opb[c] = opb_c;
+        const uint32_t inc = warp_incl_scan(nops_c, lane);
+        s_opoff[c] = inc - nops_c;
+        if (c == 31) s_opoff[32] = inc;
     }
-    if (tid < 16) { sel_s[tid] = c_sel16[tid]; cls_s[tid] = c_cls[tid]; }
+    if (tid < 16) sel_s[tid] = c_sel16[tid];
+    cls_s[tid] = cls_inc((uint32_t)tid & 15u) + cls_inc((uint32_t)tid >> 4);
     if (tid == 0) { s_nsup = 0; s_pcarry = 0; }
     __syncthreads();
 
@@ -163,18 +171,41 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
             if (e > a) toggle_range(ins, a, e, c0);
         }
         if (tid == 0) toggle_range(TM, 0, L, c0);
-        for (uint32_t c = 1 + warp; c <= nsel; c += 8) {
-            const uint32_t owi = s_ow[c];
-            const uint32_t opb = b.ow[owi].op_base, nops = b.ow_nops[owi];
-            for (uint32_t k = lane; k < nops; k += 32) {
-                const uint32_t kl = b.op_kl[opb + k], t0 = b.op_t[opb + k];
-                const uint32_t kind = kl & 3u, eff = kl >> 2;
-                if (kind == OP_M) {
-                    toggle_range(TM + c * P_CW, rm[t0], rm[t0 + eff - 1u] + 1u, c0);
-                } else if (kind == OP_I) {
-                    const uint32_t a = rm[t0 - 1u] + 1u;  // an insertion is never the first op: t0 >= 1
-                    toggle_range(TI + c * P_CW, a, a + eff, c0);
+        // all ops of all columns, flattened over the CTA; 4 ops per thread and pass so that the dependent loads
+        // (op words, then row(t) of the op's ends) of several ops are in flight together
+        {
+            const uint32_t total = s_opoff[32];
+            for (uint32_t i0 = tid; i0 < total; i0 += 4 * 256) {
+                uint32_t col[4], kl[4], t0[4], ra[4], re[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + u * 256;
+                    col[u] = 0xffffffffu;
+                    if (i < total) {
+                        uint32_t lo_c = 1, hi_c = nsel;  // largest column c with s_opoff[c] <= i
+#pragma unroll
+                        for (int it = 0; it < 5; it++) {
+                            const uint32_t mid = (lo_c + hi_c + 1) >> 1;
+                            if (s_opoff[mid] <= i) lo_c = mid; else hi_c = mid - 1;
+                        }
+                        col[u] = lo_c;
+                        const uint32_t slot = s_opb[lo_c] + (i - s_opoff[lo_c]);
+                        kl[u] = b.op_kl[slot]; t0[u] = b.op_t[slot];
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    ra[u] = re[u] = 0;
+                    if (col[u] != 0xffffffffu) {
+                        const uint32_t kind = kl[u] & 3u, eff = kl[u] >> 2;
+                        if (kind == OP_M) { ra[u] = rm[t0[u]]; re[u] = rm[t0[u] + eff - 1u] + 1u; }
+                        else if (kind == OP_I) { ra[u] = rm[t0[u] - 1u] + 1u; re[u] = ra[u] + eff; }  // never the first op: t0 >= 1
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (col[u] != 0xffffffffu && re[u] > ra[u])
+                        toggle_range(((kl[u] & 3u) == OP_M ? TM : TI) + col[u] * P_CW, ra[u], re[u], c0);
             }
         }
         __syncthreads();
@@ -272,8 +303,6 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
                         const uint32_t sel = sel_s[nib];
                         tcol[e] = __byte_perm(v, fill, sel);
                         qcol[e] = __byte_perm(qv, QUAL_EMPTY * 0x01010101u, sel);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) acc[k] += cls_s[(tcol[e] >> (8 * k)) & 0xffu];
                     }
                     // 4x4 byte transpose: tcol[e] byte k = (row k, column 4*c4+e)  ->  tw[k][c4] byte e
                     {
@@ -286,6 +315,12 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
                         qw[0][c4] = __byte_perm(q0, q1, 0x5410u); qw[1][c4] = __byte_perm(q0, q1, 0x7632u);
                         qw[2][c4] = __byte_perm(q2, q3, 0x5410u); qw[3][c4] = __byte_perm(q2, q3, 0x7632u);
                     }
+                    // class counts of the row's 4 new tokens: two pair look-ups (tokens are < 16, so a pair packs into a byte)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t pr = (tw[k][c4] | (tw[k][c4] >> 4)) & 0x00ff00ffu;
+                        acc[k] += cls_s[pr & 0xffu] + cls_s[pr >> 16];
+                    }
                 }
             }
             // ---- per-row work: second get_supported (thresh 3), majority vote, row-major stores
@@ -295,20 +330,20 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
                 for (int k = 0; k < 4; k++) {
                     const uint32_t row = row0 + k;
                     if (row >= L) break;
-                    uint32_t cnt[5];
+                    // second get_supported: >= 2 classes with >= 3 reads (adding 29 to a 6-bit field sets its bit 5 iff count >= 3)
+                    const uint32_t a6 = acc[k];
+                    const bool sup = __popc((a6 + 29u * 0x01041041u) & 0x20820820u) >= 2;
+                    // two most common classes, stable on ties (A<C<G<T<*): keys (count << 3 | 7 - class), top two by a max/min chain
+                    uint32_t ka = ((a6 & 63u) << 3) | 7u, kb = 0u;
 #pragma unroll
-                    for (int q = 0; q < 5; q++) cnt[q] = (acc[k] >> (5 * q)) & 31u;
-                    const uint32_t ns = (cnt[0] >= 3) + (cnt[1] >= 3) + (cnt[2] >= 3) + (cnt[3] >= 3) + (cnt[4] >= 3);
-                    const bool sup = ns >= 2;
-                    // two most common, stable on ties (A<C<G<T<*)
-                    uint32_t b0 = 0;
-#pragma unroll
-                    for (int q = 1; q < 5; q++) if (cnt[q] > cnt[b0]) b0 = q;
-                    uint32_t b1 = b0 == 0 ? 1 : 0;
-#pragma unroll
-                    for (int q = 0; q < 5; q++) if ((uint32_t)q != b0 && (uint32_t)q != b1 && cnt[q] > cnt[b1]) b1 = q;
+                    for (int q = 1; q < 5; q++) {
+                        const uint32_t kq = (((a6 >> (6 * q)) & 63u) << 3) | (uint32_t)(7 - q);
+                        kb = max(kb, min(ka, kq));
+                        ka = max(ka, kq);
+                    }
+                    const uint32_t b0 = 7u - (ka & 7u), b1 = 7u - (kb & 7u), m0 = ka >> 3, m1 = kb >> 3;
                     const uint32_t tb = tw[k][0] & 0xffu;  // target column, token 0..4
-                    const uint32_t base = (cnt[b0] < 2 || (cnt[b0] == cnt[b1] && (b0 == tb || b1 == tb))) ? tb : b0;
+                    const uint32_t base = (m0 < 2u || (m0 == m1 && (b0 == tb || b1 == tb))) ? tb : b0;
                     const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
                     b.row_emit[rowbase + row] = (uint8_t)(emit | (sup ? 0x80u : 0u));
                     supm |= (sup ? 1u : 0u) << k;
@@ -356,7 +391,7 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
 
 size_t pileup_smem() {
     return (size_t)2 * 32 * P_CW * 4 + (size_t)P_CW * 4 + (size_t)32 * P_CW * 2 + (size_t)P_CW * 2 + 32 * (sizeof(ColA) + sizeof(ColB) + sizeof(ColC)) +
-           32 * 4 + 64;
+           (16 + 256) * 4 + 64;
 }
 
 cudaError_t pileup_configure() {

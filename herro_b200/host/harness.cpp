@@ -7,6 +7,7 @@
 //   (src/lib.rs:198-199,267-291) and, when the producers are done, hb_flush()es.
 //
 // There is no Rust toolchain in the build image; tests and bench.py drive this through ctypes.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -18,6 +19,42 @@
 #include "../../include/herro_b200.h"
 
 extern "C" {
+
+// 2-bit packing of the read store, HAECSeq layout (src/haec_io.rs:121-136: 32 bases per u64, A0 C1 G2 T3, base i of a word at
+// bits [2i, 2i+2)); `threads` workers over reads.  words must hold woff[n] entries (woff[i] = sum of ceil(len/32) before read i).
+// Returns 0, or -1 if a base is not one of ACGTacgt (the reference's packing is undefined for it).
+int hbh_pack_2bit(const uint8_t* seqs, const uint64_t* off, uint32_t n_reads, uint64_t* words, const uint64_t* woff, int threads) {
+    static const auto lut = [] {
+        std::vector<uint8_t> t(256, 255);
+        t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+        return t;
+    }();
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t i0 = next.fetch_add(64);
+            if (i0 >= n_reads) break;
+            for (uint32_t i = i0; i < std::min(n_reads, i0 + 64); i++) {
+                const uint8_t* s = seqs + off[i];
+                const uint64_t len = off[i + 1] - off[i];
+                uint64_t* w = words + woff[i];
+                for (uint64_t b = 0; b < len; b += 32) {
+                    const uint64_t m = std::min<uint64_t>(32, len - b);
+                    uint64_t v = 0;
+                    uint8_t any = 0;
+                    for (uint64_t k = 0; k < m; k++) { const uint8_t c = lut[s[b + k]]; any |= c; v |= (uint64_t)(c & 3) << (2 * k); }
+                    if (any > 3) bad = 1;
+                    w[b >> 5] = v;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < (threads > 0 ? threads : 1); i++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    return bad.load() ? -1 : 0;
+}
 
 // Parallel host windowing (what the Rust feature threads do before submitting): fills ow_off[n_t+1]
 // and, if ow_out != NULL (cap records), the windows of targets [t_begin, t_end) back to back.

@@ -39,7 +39,7 @@ def run_oracle(rs, model, window_size=4096, batch_size=64, targets=None, with_fo
         from oracle import forward_ref
         cfg, tensors = hbw.load_blob(model)
         net = forward_ref.from_weights(cfg, tensors)
-    out = dict(windows={}, logits={}, segments={})
+    out = dict(windows={}, logits={}, segments={}, targets={}, win_index={})
     targets = range(rs.n) if targets is None else targets
     for t in targets:
         ovl, cigs = rs.target_alns(t)
@@ -47,8 +47,10 @@ def run_oracle(rs, model, window_size=4096, batch_size=64, targets=None, with_fo
             continue  # reads that never appear as a PAF target produce no record (H6)
         T = po.Target(reads, t, ovl, cigs, window_size, batch_size)
         wins = T.windows()
+        out["targets"][t] = T
         for i, w in enumerate(wins):
             out["windows"][(t, w.wid)] = w
+            out["win_index"][(t, w.wid)] = i
         if with_forward:
             for b in range(T.n_batches):
                 B = T.batch(b)
@@ -98,8 +100,10 @@ def run_product(rs, model, window_size=4096, batch_size=64, targets=None, keep_d
 
 
 def compare(ora, got, logits_tol=1e-3, check_windows=True):
+    """Asserts parity; returns dict(reads, windows, tie_reads, max_logit_diff)."""
     # segments: byte-identical per read; None (read omitted) on both sides
     assert set(ora["segments"].keys()) == set(got["segments"].keys())
+    max_diff = 0.0
     if check_windows and got["windows"]:
         for key, w in ora["windows"].items():
             g = got["windows"][key]
@@ -113,5 +117,30 @@ def compare(ora, got, logits_tol=1e-3, check_windows=True):
                 info, bl = ora["logits"][key]
                 assert np.allclose(g["info_logits"], info, atol=logits_tol, rtol=0), (key, np.abs(g["info_logits"] - info).max())
                 assert np.allclose(g["bases_logits"], bl, atol=logits_tol, rtol=0), (key, np.abs(g["bases_logits"] - bl).max())
+                if len(bl):
+                    max_diff = max(max_diff, float(np.abs(g["bases_logits"] - bl).max()), float(np.abs(g["info_logits"] - info).max()))
+    n_tie_reads = 0
     for rid, segs in ora["segments"].items():
-        assert got["segments"][rid] == segs, f"segments differ for read {rid}"
+        if got["segments"][rid] == segs:
+            continue
+        # The corrected bases are argmaxes of logits that agree only to `logits_tol`: where the oracle's two largest logits
+        # of a position are closer than that, the two sides may legitimately pick different bases.  Accept such a read iff
+        # (a) it has such a near-tie and (b) the oracle's own consensus() fed with the product's logits reproduces the
+        # product's segments byte for byte (so everything but the tie-break is identical).
+        assert logits_tol is not None and got["windows"] and rid in ora.get("targets", {}), f"segments differ for read {rid}"
+        T = ora["targets"][rid]
+        gap = np.inf
+        for (t, wid), i in ora["win_index"].items():
+            if t != rid:
+                continue
+            if (t, wid) in ora["logits"]:
+                bl = np.sort(ora["logits"][(t, wid)][1], axis=1)
+                if len(bl):
+                    gap = min(gap, float((bl[:, -1] - bl[:, -2]).min()))
+                g = got["windows"][(t, wid)]
+                T.set_logits(i, g["info_logits"], g["bases_logits"])
+        assert gap < 2 * logits_tol, f"segments differ for read {rid} without a near-tie in the logits (min top-2 gap {gap})"
+        assert T.consensus() == got["segments"][rid], f"segments differ for read {rid} beyond argmax ties"
+        n_tie_reads += 1
+    assert n_tie_reads <= max(1, len(ora["segments"]) // 20), f"{n_tie_reads} reads differ through logit near-ties: too many to be ties"
+    return dict(reads=len(ora["segments"]), windows=len(ora["windows"]), tie_reads=n_tie_reads, max_logit_diff=max_diff)

@@ -106,6 +106,7 @@ struct OpList {
 extern "C" {
 
 struct synth_set;  // opaque = Set
+void synth_make_alns(void* h, uint32_t tgt_begin, uint32_t tgt_end, uint32_t tgt_stride, uint32_t tgt_phase, uint32_t n_threads);
 
 void* synth_generate(uint64_t seed, uint64_t genome_len, uint32_t n_reads, uint32_t mean_len, uint32_t sd_len,
                      uint32_t min_len, uint32_t max_len, double sub, double ins, double del, double hp_boost,
@@ -244,6 +245,19 @@ void* synth_generate(uint64_t seed, uint64_t genome_len, uint32_t n_reads, uint3
         for (auto& t : th) t.join();
     }
 
+    S->p.min_len = min_len; S->p.max_len = max_len;
+    if (tgt_end > tgt_begin) synth_make_alns(S, tgt_begin, tgt_end, tgt_stride, tgt_phase, n_threads);
+    else { S->aln_off.assign(n_reads + 1, 0); S->cig_off.assign(1, 0); }
+    return S;
+}
+
+// Alignments (grouped by target) for targets t in [tgt_begin, tgt_end) with t % tgt_stride == tgt_phase, replacing whatever
+// alignments the set held.  Deterministic: the same target always gets the same alignments, whichever subset is asked for.
+void synth_make_alns(void* h, uint32_t tgt_begin, uint32_t tgt_end, uint32_t tgt_stride, uint32_t tgt_phase, uint32_t n_threads) {
+    Set* S = (Set*)h;
+    const uint32_t n_reads = (uint32_t)S->reads.size();
+    const uint32_t min_ovl = S->p.min_ovl;
+    S->ovl9.clear(); S->cigars.clear(); S->cig_off.clear();
     // ---- overlaps ----------------------------------------------------------------------
     std::vector<uint32_t> order(n_reads);
     for (uint32_t i = 0; i < n_reads; i++) order[i] = i;
@@ -332,12 +346,12 @@ void* synth_generate(uint64_t seed, uint64_t genome_len, uint32_t n_reads, uint3
         PerTarget().cig.swap(P.cig);
         std::vector<uint32_t>().swap(P.ovl9);
     }
-    // free the per-position maps (large)
-    for (auto& R : S->reads) {
-        std::vector<uint8_t>().swap(R.ev);
-        std::vector<uint32_t>().swap(R.ckpt);
-    }
-    return S;
+}
+
+// read lengths (so that a caller can shard targets before asking for alignments)
+void synth_read_lens(void* h, uint32_t* out) {
+    Set* S = (Set*)h;
+    for (size_t i = 0; i < S->reads.size(); i++) out[i] = S->reads[i].len();
 }
 
 void synth_free(void* h) { delete (Set*)h; }

@@ -62,11 +62,7 @@ class ReadSet:
         return int(self.off[-1])
 
 
-def generate(n_reads: int, mean_len: int, *, profile="r10", seed=1, coverage=40.0, sd_frac=0.10, min_len=None,
-             max_len=None, het_snp=1e-3, het_indel=1e-4, long_del=2e-6, min_ovl=2048, genome_len=None,
-             threads=None, targets=None, target_stride=(1, 0)) -> ReadSet:
-    """targets=(begin, end) / target_stride=(stride, phase): build alignments only for those target reads (all reads are
-    always generated, so the read store and every query are those of the full set)."""
+def _lib():
     build()
     L = C.CDLL(_LIB)
     L.synth_generate.restype = C.c_void_p
@@ -78,30 +74,73 @@ def generate(n_reads: int, mean_len: int, *, profile="r10", seed=1, coverage=40.
     vp = C.c_void_p
     L.synth_get_reads.argtypes = [vp] + [vp] * 6
     L.synth_get_alns.argtypes = [vp] + [vp] * 4
-    sub, ins, dele, hpb = PROFILES[profile]
-    if genome_len is None:
-        genome_len = max(int(n_reads * mean_len / coverage), mean_len * 2)
-    min_len = min_len if min_len is not None else max(int(mean_len * 0.5), 1)
-    max_len = max_len if max_len is not None else int(mean_len * 2)
-    threads = threads or os.cpu_count() or 1
-    tb, te = targets if targets is not None else (0, n_reads)
-    h = L.synth_generate(seed, genome_len, n_reads, mean_len, int(mean_len * sd_frac), min_len, max_len, sub, ins,
-                         dele, hpb, het_snp, het_indel, long_del, min_ovl, threads, tb, te, target_stride[0], target_stride[1])
-    try:
+    L.synth_make_alns.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.synth_make_alns.restype = None
+    L.synth_read_lens.argtypes = [vp, vp]
+    L.synth_read_lens.restype = None
+    return L
+
+
+class Generator:
+    """Two-phase use of the generator: reads first (their lengths decide the sharding), then the alignments of a chosen
+    target subset.  `generate()` below is the one-shot form."""
+
+    def __init__(self, n_reads: int, mean_len: int, *, profile="r10", seed=1, coverage=40.0, sd_frac=0.10, min_len=None,
+                 max_len=None, het_snp=1e-3, het_indel=1e-4, long_del=2e-6, min_ovl=2048, genome_len=None, threads=None):
+        self.L = _lib()
+        sub, ins, dele, hpb = PROFILES[profile]
+        if genome_len is None:
+            genome_len = max(int(n_reads * mean_len / coverage), mean_len * 2)
+        min_len = min_len if min_len is not None else max(int(mean_len * 0.5), 1)
+        max_len = max_len if max_len is not None else int(mean_len * 2)
+        self.threads = threads or os.cpu_count() or 1
+        self.n = n_reads
+        self.h = self.L.synth_generate(seed, genome_len, n_reads, mean_len, int(mean_len * sd_frac), min_len, max_len, sub, ins,
+                                       dele, hpb, het_snp, het_indel, long_del, min_ovl, self.threads, 0, 0, 1, 0)
+
+    def read_lens(self) -> np.ndarray:
+        out = np.zeros(self.n, np.uint32)
+        self.L.synth_read_lens(self.h, out.ctypes.data)
+        return out
+
+    def readset(self, targets=None, target_stride=(1, 0)) -> ReadSet:
+        """All reads + the alignments of targets [begin, end) with t % stride == phase (default: every target)."""
+        L, h = self.L, self.h
+        tb, te = targets if targets is not None else (0, self.n)
+        L.synth_make_alns(h, tb, te, target_stride[0], target_stride[1], self.threads)
         sz = (C.c_uint64 * 4)()
         L.synth_sizes(h, sz)
-        n, tb, na, cb = (int(x) for x in sz)
-        seqs = np.zeros(tb, np.uint8); quals = np.zeros(tb, np.uint8); off = np.zeros(n + 1, np.uint64)
+        n, nb, na, cb = (int(x) for x in sz)
+        seqs = np.zeros(nb, np.uint8); quals = np.zeros(nb, np.uint8); off = np.zeros(n + 1, np.uint64)
         strand = np.zeros(n, np.uint8); hap = np.zeros(n, np.uint8); gs = np.zeros(n, np.uint64)
         L.synth_get_reads(h, seqs.ctypes.data, quals.ctypes.data, off.ctypes.data, strand.ctypes.data,
                           hap.ctypes.data, gs.ctypes.data)
         aln_off = np.zeros(n + 1, np.uint64); ovl9 = np.zeros((max(na, 1), 9), np.uint32)
         cig_off = np.zeros(na + 1, np.uint64); cig = np.zeros(max(cb, 1), np.uint8)
         L.synth_get_alns(h, aln_off.ctypes.data, ovl9.ctypes.data, cig_off.ctypes.data, cig.ctypes.data)
+        ids = [f"read_{i:06d}" for i in range(n)]
+        return ReadSet(ids, seqs, quals, off, aln_off, ovl9[:na], cig_off, cig[:cb], strand, hap)
+
+    def close(self):
+        if self.h:
+            self.L.synth_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def generate(n_reads: int, mean_len: int, *, targets=None, target_stride=(1, 0), **kw) -> ReadSet:
+    """targets=(begin, end) / target_stride=(stride, phase): build alignments only for those target reads (all reads are
+    always generated, so the read store and every query are those of the full set)."""
+    g = Generator(n_reads, mean_len, **kw)
+    try:
+        return g.readset(targets, target_stride)
     finally:
-        L.synth_free(h)
-    ids = [f"read_{i:06d}" for i in range(n)]
-    return ReadSet(ids, seqs, quals, off, aln_off, ovl9[:na], cig_off, cig[:cb], strand, hap)
+        g.close()
 
 
 def write_fastq(rs: ReadSet, path: str, descriptions=None):
