@@ -84,6 +84,7 @@ def load_library():
     L.hb_submit_target.argtypes = [vp, u32, u32, vp, u32, vp, u32]
     L.hb_submit_alignments.argtypes = [vp, u32, vp, u32]
     L.hb_extract_windows.argtypes = [vp, u32, u32, u32, vp, u32, u32p]
+    L.hb_window_range.argtypes = [vp, u32, u32, u32p, u32p]
     L.hb_flush.argtypes = [vp]
     L.hb_set_launch_targets.argtypes = [vp, u32]
     L.hb_set_kernel_timing.argtypes = [vp, C.c_int]
@@ -102,7 +103,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_window_range", "hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -151,6 +152,16 @@ def extract_windows(overlaps: np.ndarray, window_size: int, n_windows: int) -> n
     if rc != 0:
         raise HerroError(rc, "alignment on which the reference would panic")
     return out[:n.value]
+
+
+def window_range(overlap: np.ndarray, window_size: int, n_windows: int):
+    """(first, end) of the windows one alignment (a 1-element OVERLAP_DTYPE array) contributes to (hb_window_range)."""
+    L = load_library()
+    a, b = C.c_uint32(), C.c_uint32()
+    rc = L.hb_window_range(overlap.ctypes.data, window_size, n_windows, C.byref(a), C.byref(b))
+    if rc != 0:
+        raise HerroError(rc, "alignment on which the reference would panic")
+    return a.value, b.value
 
 
 @dataclass

@@ -20,19 +20,25 @@ constexpr uint32_t OWF_BAD = 2;         // input on which the reference would pa
 
 constexpr uint32_t OP_M = 0, OP_I = 2, OP_D = 3;
 
+constexpr uint32_t RAW_NONE = 0xffffffffu;
+
 struct DevOverlap {  // Overlap (src/overlaps.rs:44-55) reduced to what the path reads
     uint32_t qid, qstart, qend, strand;
     uint64_t cig_off;
     uint32_t cig_len;
     uint32_t tgt;  // target index inside the batch
+    uint32_t tstart, tend;  // target span (device windowing, windowing_dev.cu)
+    uint32_t raw_base;      // first slot of the alignment's raw-op arrays; RAW_NONE: its OverlapWindows came from the host
+    uint32_t pad;
 };
 
 struct DevOW {  // OverlapWindow (src/windowing.rs:6-16)
     uint32_t ovl;  // batch-global overlap index
     uint32_t win;  // batch-global window index
     uint32_t tstart, qstart, qend;
-    uint32_t csi, cso, cei, ceo;
-    uint32_t op_base;  // first slot in the tokenised-op arrays
+    uint32_t csi, cso, cei, ceo;  // host windows: byte indices into the CIGAR text (csi, cei) / base offsets; device windows
+                                  // (windowing_dev.cu): csi / cei are the indices of the first / last op of the alignment's raw-op array
+    uint32_t op_base;  // first slot in the tokenised-op arrays (device windows: assigned by a scan on the device)
 };
 
 struct DevWin {
@@ -67,7 +73,17 @@ struct BatchView {
     const DevWin* win;
     const DevOverlap* ovl;
     const DevOW* ow;
+    DevOW* ow_mut;     // the same array: device windowing fills in the OverlapWindow fields and op_base
     const uint8_t* cig;
+    // device windowing (windowing_dev.cu): every alignment's CIGAR tokenised once, with inclusive target / query prefix sums
+    uint32_t* raw_kl;  // kind | len << 2
+    uint32_t* raw_t;   // target bases consumed up to and including the op (relative to overlap.tstart)
+    uint32_t* raw_q;   // query bases consumed up to and including the op
+    uint32_t* aln_nops;   // [n_ovl]
+    uint32_t* aln_flags;  // [n_ovl] OWF_BAD: malformed CIGAR, or one that disagrees with the PAF coordinates
+    uint64_t* ow_opoff;   // [n_ow] exclusive scan of the op counts of device-windowed overlap-windows
+    uint32_t op_base_dev; // their op slots start here (after the host-assigned ones)
+    uint32_t n_raw;       // alignments windowed on the device in this batch
     // tokenised ops
     uint32_t* op_kl;  // kind | eff_len << 2
     uint32_t* op_t;   // window-relative target position at op start
@@ -118,7 +134,7 @@ struct BatchView {
     uint32_t* counters;  // [0] total rows overflow flag, [1] n_sup_total, [2] total_out, [3] total_rows lo, ...
 };
 
-constexpr int CNT_OVERFLOW = 0, CNT_TOTAL_ROWS = 2, CNT_TOTAL_OUT = 4, CNT_NSUP = 6, CNT_N = 8;  // 64-bit totals use 2 slots
+constexpr int CNT_OVERFLOW = 0, CNT_TOTAL_ROWS = 2, CNT_TOTAL_OUT = 4, CNT_NSUP = 6, CNT_DEV_OPS = 8, CNT_N = 10;  // 64-bit totals use 2 slots
 
 constexpr uint32_t TERR_BAD_INPUT = 1, TERR_TOO_MANY_COLS = 2;
 

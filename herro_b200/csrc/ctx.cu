@@ -176,10 +176,13 @@ struct HostBatch {
     PinVec<DevOverlap> ovl;
     PinVec<DevOW> ow;
     PinVec<uint8_t> cig;
-    uint64_t op_cap = 0;
+    uint64_t op_cap = 0;      // op slots of host-windowed overlap-windows (assigned here)
+    uint64_t raw_cap = 0;     // raw-op slots of device-windowed alignments (cig_len / 2 + 1 each)
+    uint64_t dev_op_cap = 0;  // bound on the op slots their overlap-windows need (assigned by a scan on the device)
+    uint32_t n_raw = 0;       // device-windowed alignments
     HostBatch() {}
     explicit HostBatch(int dev) { tgt.dev = win.dev = ovl.dev = ow.dev = cig.dev = dev; }
-    void clear() { tgt.clear(); win.clear(); ovl.clear(); ow.clear(); cig.clear(); op_cap = 0; }
+    void clear() { tgt.clear(); win.clear(); ovl.clear(); ow.clear(); cig.clear(); op_cap = raw_cap = dev_op_cap = 0; n_raw = 0; }
 };
 
 struct Result {
@@ -237,17 +240,19 @@ struct hb_ctx {
         DevBuf d_ovl_n, d_ovl_tot, d_ovl_score, d_sel_ow, d_w_nsel, d_rowmap, d_w_L, d_w_rowbase, d_w_nsup, d_w_reflmax;
         DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
         DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info, d_big_key, d_big_cand, d_big_score;
+        DevBuf d_raw_kl, d_raw_t, d_raw_q, d_aln_nops, d_aln_flags, d_ow_opoff;  // device windowing (windowing_dev.cu)
         uint64_t rows_cap = 0;
         uint64_t seen_sizes = 0;  // version of hb_ctx::lane_sizes this lane has been pre-sized to
         LastLaunch last;
         std::thread worker;
-        static constexpr int N_DEV = 44;
+        static constexpr int N_DEV = 50;
         void all_bufs(DevBuf* (&out)[N_DEV]) {
             DevBuf* bufs[N_DEV] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
                                    &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
                                    &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
                                    &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
-                                   &d_counters, &d_ws, &d_logits, &d_info, &d_big_key, &d_big_cand, &d_big_score};
+                                   &d_counters, &d_ws, &d_logits, &d_info, &d_big_key, &d_big_cand, &d_big_score,
+                                   &d_raw_kl, &d_raw_t, &d_raw_q, &d_aln_nops, &d_aln_flags, &d_ow_opoff};
             for (int i = 0; i < N_DEV; i++) out[i] = bufs[i];
         }
         void bind_stream() { DevBuf* bufs[N_DEV]; all_bufs(bufs); for (DevBuf* b : bufs) b->st = stream; }
@@ -291,6 +296,7 @@ struct hb_ctx {
     uint64_t alloc_base[3] = {0, 0, 0};     // g_allocs / g_alloc_ns / g_submit_wait_ns at the last hb_reset_stats
     uint64_t generation = 0;  // distinguishes contexts that reuse an address (thread-local slot cache)
     // debugging aids read from the environment once, in hb_create
+    bool host_windowing = false;     // HERRO_B200_HOST_WINDOWING: hb_submit_alignments runs extract_windows on the host (A-B test)
     bool pileup_v1 = false;          // HERRO_B200_PILEUP_V1: the former position-walk pileup kernel (A-B parity test)
     uint32_t arena_rows_per_win = 0; // HERRO_B200_ARENA_ROWS: initial row-arena rows per window (default 1.5 W); tests shrink it
                                      // to force the overflow -> regrow -> relaunch path
@@ -523,7 +529,12 @@ int ensure_batch_buffers(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     CK(L->d_ovl.ensure(std::max<size_t>(no, 1) * sizeof(DevOverlap)));
     CK(L->d_ow.ensure(std::max<size_t>(now_, 1) * sizeof(DevOW)));
     CK(L->d_cig.ensure(std::max<size_t>(hbt.cig.size(), 16)));
-    const size_t opc = std::max<uint64_t>(hbt.op_cap, 1);
+    const size_t opc = std::max<uint64_t>(hbt.op_cap + hbt.dev_op_cap, 1);
+    if (opc >= 0xffffffffull) return fail(ctx, HB_ERR_CAPACITY, "batch too large: more than 2^32 CIGAR ops (lower launch_targets)");
+    const size_t rawc = std::max<uint64_t>(hbt.raw_cap, 1);
+    CK(L->d_raw_kl.ensure(rawc * 4));
+    CK(L->d_raw_t.ensure(rawc * 4));
+    CK(L->d_raw_q.ensure(rawc * 4));
     CK(L->d_op_kl.ensure(opc * 4));
     CK(L->d_op_t.ensure(opc * 4));
     CK(L->d_op_q.ensure(opc * 4));
@@ -536,12 +547,15 @@ int ensure_batch_buffers(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     CK(L->d_big_key.ensure(ow1 * 4));
     CK(L->d_big_cand.ensure(ow1 * 4));
     CK(L->d_big_score.ensure(ow1 * 8));
+    CK(L->d_ow_opoff.ensure(ow1 * 8));
     CK(L->d_w_n1.ensure(nw * 4));
     CK(L->d_w_S.ensure(nw * 4));
     const size_t no1 = std::max<size_t>(no, 1);
     CK(L->d_ovl_n.ensure(no1 * 4));
     CK(L->d_ovl_tot.ensure(no1 * 4));
     CK(L->d_ovl_score.ensure(no1 * 8));
+    CK(L->d_aln_nops.ensure(no1 * 4));
+    CK(L->d_aln_flags.ensure(no1 * 4));
     CK(L->d_sel_ow.ensure(nw * TOP_K * 4));
     CK(L->d_w_nsel.ensure(nw * 4));
     CK(L->d_rowmap.ensure(nw * (size_t)(W + 1) * 4));
@@ -576,6 +590,13 @@ void set_view_ptrs(hb_ctx* ctx, hb_ctx::Lane* L, BatchView& b) {
     b.win = L->d_win.as<DevWin>();
     b.ovl = L->d_ovl.as<DevOverlap>();
     b.ow = L->d_ow.as<DevOW>();
+    b.ow_mut = L->d_ow.as<DevOW>();
+    b.raw_kl = L->d_raw_kl.as<uint32_t>();
+    b.raw_t = L->d_raw_t.as<uint32_t>();
+    b.raw_q = L->d_raw_q.as<uint32_t>();
+    b.aln_nops = L->d_aln_nops.as<uint32_t>();
+    b.aln_flags = L->d_aln_flags.as<uint32_t>();
+    b.ow_opoff = L->d_ow_opoff.as<uint64_t>();
     b.cig = L->d_cig.as<uint8_t>();
     b.op_kl = L->d_op_kl.as<uint32_t>();
     b.op_t = L->d_op_t.as<uint32_t>();
@@ -626,6 +647,8 @@ BatchView make_view(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     b.n_ow = (uint32_t)hbt.ow.size();
     b.batch_size = ctx->opt.batch_size;
     b.rows_cap = L->rows_cap;
+    b.n_raw = hbt.n_raw;
+    b.op_base_dev = (uint32_t)hbt.op_cap;
     set_view_ptrs(ctx, L, b);
     return b;
 }
@@ -793,7 +816,9 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
             uint64_t cb = 0;
             for (uint32_t c = 0; c < h_nsel[w]; c++) {
                 const DevOW& ow = hbt.ow[h_sel[(size_t)w * TOP_K + c]];
-                cb += ow.cei - ow.csi;
+                const DevOverlap& ov = hbt.ovl[ow.ovl];
+                if (ov.raw_base == RAW_NONE) cb += ow.cei - ow.csi;
+                else cb += (uint64_t)ov.cig_len * W / std::max<uint32_t>(ov.tend - ov.tstart, W);  // device-windowed: its share of the CIGAR
             }
             algo += (uint64_t)(h_nsel[w] + 1) * ((dw.len + 3) / 4 + dw.len) + cb + 2ull * R_COLS * h_L[w];
         }
@@ -1010,7 +1035,37 @@ struct PreparedTarget {
     std::vector<uint32_t> win_begin;  // [n_windows+1] CSR of the bucketed overlap-windows
     std::vector<DevOW> ow;            // bucketed by window, push order kept; ovl/win indices target-local
     uint64_t cig_bytes = 0;
+    bool raw = false;                 // device windowing: `ow` is only the (overlap, window) skeleton
+    std::vector<uint32_t> aln_now;    // raw: overlap-windows per alignment (0: the alignment contributes nothing, its CIGAR is not shipped)
 };
+
+// Which windows an alignment contributes to — the coordinate-only part of windowing::extract_windows
+// (src/windowing.rs:53-125,260-272).  Emitted windows are the contiguous range [wa, we).
+// Returns 0, or -1 where the reference would panic (inverted coordinates, a window index past the target's last window,
+// the trailing-window unwrap of a None start state).
+int skeleton_for_alignment(const hb_overlap& o, uint32_t W, uint32_t n_windows, uint32_t& wa, uint32_t& we) {
+    wa = we = 0;
+    if (o.tend < o.tstart || o.qend < o.qstart) return -1;
+    if (o.tend - o.tstart < W || o.qend - o.qstart < W) return 0;          // :53-57
+    const uint32_t edge = (uint32_t)(0.1f * (float)W);                      // :65
+    if (o.tlen < edge) return -1;
+    const uint32_t tail_thresh = o.tlen - edge;
+    const uint32_t first_w = o.tstart < edge ? 0 : (o.tstart + W - 1) / W;  // :75-79
+    const uint32_t last_w = o.tend > tail_thresh ? (o.tend - 1) / W + 1 : o.tend / W;  // :81-85
+    if (last_w <= first_w) return 0;                                       // :106
+    const bool open0 = (o.tstart % W == 0) || (o.tstart < edge);            // :120-125
+    const uint32_t w_cur = o.tstart / W, w_new = o.tend / W;
+    const uint32_t a = open0 ? w_cur : w_cur + 1;  // a window is emitted at every boundary crossed once a start state exists
+    uint32_t e = w_new;
+    if (o.tend > tail_thresh && o.tend % W != 0) {  // trailing partial window
+        if (!open0 && w_new == w_cur) return -1;    // the reference unwraps a None start state here
+        e = w_new + 1;
+    }
+    if (e <= a) return 0;
+    if (e > n_windows) return -1;
+    wa = a; we = e;
+    return 0;
+}
 
 int prepare_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
                    const hb_overlap_window* ow, uint32_t n_ow, PreparedTarget& P) {
@@ -1057,8 +1112,22 @@ int append_target(hb_ctx* ctx, HostBatch& hbt, const PreparedTarget& P, const hb
         !hbt.ow.resize(ow_base + n_ow) || !hbt.tgt.reserve(t_idx + 1))
         return fail(ctx, HB_ERR_CAPACITY, "out of pinned host memory");
     for (uint32_t i = 0; i < n_ovl; i++) {
-        hbt.ovl.push_back(DevOverlap{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx});
-        hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len);
+        DevOverlap d{ovl[i].qid, ovl[i].qstart, ovl[i].qend, ovl[i].strand, (uint64_t)hbt.cig.size(), ovl[i].cigar_len, t_idx,
+                     ovl[i].tstart, ovl[i].tend, RAW_NONE, 0};
+        if (P.raw) {
+            if (P.aln_now[i] == 0) {
+                d.cig_len = 0;  // contributes to no window: its CIGAR stays on the host
+            } else {
+                d.raw_base = (uint32_t)hbt.raw_cap;
+                hbt.raw_cap += ovl[i].cigar_len / 2 + 1;
+                hbt.dev_op_cap += ovl[i].cigar_len / 2 + 1 + P.aln_now[i];  // every op once + one shared op per boundary
+                hbt.n_raw++;
+                hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len);
+            }
+        } else {
+            hbt.cig.append(ovl[i].cigar, ovl[i].cigar_len);
+        }
+        hbt.ovl.push_back(d);
     }
     for (uint32_t w = 0; w < P.n_windows; w++) {
         DevWin d{};
@@ -1073,12 +1142,36 @@ int append_target(hb_ctx* ctx, HostBatch& hbt, const PreparedTarget& P, const hb
         DevOW d = P.ow[i];
         d.ovl += ovl_base;
         d.win += win_base;
-        d.op_base = (uint32_t)opc;
-        opc += (d.cei - d.csi) / 2 + 1;
+        if (P.raw) {
+            d.op_base = 0;  // assigned on the device
+        } else {
+            d.op_base = (uint32_t)opc;
+            opc += (d.cei - d.csi) / 2 + 1;
+        }
         hbt.ow[ow_base + i] = d;
     }
     hbt.op_cap = opc;
     hbt.tgt.push_back(DevTarget{P.rid, win_base, win_base + P.n_windows, ovl_base, ovl_base + n_ovl});
+    return HB_OK;
+}
+
+// Stage one prepared target in the calling thread's batch and hand the batch over when it is full.
+int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, uint32_t n_ovl) {
+    hb_ctx::ThreadSlot* slot = my_slot(ctx);
+    if (slot->batch.tgt.cap == 0) acquire_batch(ctx, slot->batch);
+    std::string local_err;
+    t_err_sink = &local_err;
+    const int rc = append_target(ctx, slot->batch, P, ovl, n_ovl);
+    t_err_sink = nullptr;
+    if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
+    // `launch_targets` is shared by the submitting threads: each stages launch_targets / n_threads targets per launch,
+    // so the targets in flight (and the latency to the first launch) do not grow with the thread count
+    const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
+    const uint32_t thr = std::min(lt, std::max(32u, lt / ns));
+    if (slot->batch.tgt.size() >= thr) {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        enqueue_batch(ctx, lk, slot->batch);
+    }
     return HB_OK;
 }
 
@@ -1119,6 +1212,7 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (const char* e = getenv("HERRO_B200_LANES")) ctx->n_lanes = std::min(std::max(atoi(e), 1), (int)hb_ctx::MAX_LANES);
     // debugging aids / A-B parity tests: read here once, never on the launch path
     ctx->pileup_v1 = getenv("HERRO_B200_PILEUP_V1") != nullptr;
+    ctx->host_windowing = getenv("HERRO_B200_HOST_WINDOWING") != nullptr;
     if (const char* e = getenv("HERRO_B200_ARENA_ROWS")) ctx->arena_rows_per_win = (uint32_t)std::max(atoi(e), 1);
     ctx->wt.no_fuse_ln = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;
     ctx->wt.no_fuse_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;
@@ -1255,21 +1349,7 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
         t_err_sink = nullptr;
         if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
     }
-    hb_ctx::ThreadSlot* slot = my_slot(ctx);
-    if (slot->batch.tgt.cap == 0) acquire_batch(ctx, slot->batch);
-    t_err_sink = &local_err;
-    const int rc = append_target(ctx, slot->batch, P, ovl, n_ovl);
-    t_err_sink = nullptr;
-    if (rc) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = local_err; return rc; }
-    // `launch_targets` is shared by the submitting threads: each stages launch_targets / n_threads targets per launch,
-    // so the targets in flight (and the latency to the first launch) do not grow with the thread count
-    const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
-    const uint32_t thr = std::min(lt, std::max(32u, lt / ns));
-    if (slot->batch.tgt.size() >= thr) {
-        std::unique_lock<std::mutex> lk(ctx->mu);
-        enqueue_batch(ctx, lk, slot->batch);
-    }
-    return HB_OK;
+    return stage_target(ctx, P, ovl, n_ovl);
 }
 
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl) {
@@ -1280,13 +1360,45 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
     if (n_ovl && !ovl) return fail_locked(HB_ERR_ARG, "null array");
     const uint32_t W = ctx->opt.window_size;
     const uint32_t n_windows = (ctx->read_len[rid] + W - 1) / W;
-    std::vector<hb_overlap_window> ows;  // windowing runs outside the lock: feature threads do it in parallel
-    for (uint32_t i = 0; i < n_ovl; i++) {
-        if (ovl[i].tid != rid) return fail_locked(HB_ERR_ARG, "overlap.tid != rid");
-        if (host_extract_windows(ovl[i], i, W, n_windows, ows) != 0)
-            return fail_locked(HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
+    if (ctx->host_windowing) {  // A-B path: extract_windows on the calling thread, then the hb_submit_target route
+        std::vector<hb_overlap_window> ows;
+        for (uint32_t i = 0; i < n_ovl; i++) {
+            if (ovl[i].tid != rid) return fail_locked(HB_ERR_ARG, "overlap.tid != rid");
+            if (host_extract_windows(ovl[i], i, W, n_windows, ows) != 0)
+                return fail_locked(HB_ERR_INPUT, "malformed alignment (CIGAR / coordinates) for target " + std::to_string(rid));
+        }
+        return hb_submit_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
     }
-    return hb_submit_target(ctx, rid, n_windows, ovl, n_ovl, ows.data(), (uint32_t)ows.size());
+    // Device windowing (windowing_dev.cu): the host only lays out which (alignment, window) pairs exist — a function of the PAF
+    // coordinates — and ships the CIGARs; a CIGAR that is malformed or disagrees with its coordinates fails this target at
+    // hb_poll_corrected (HB_ERR_INPUT) instead of here.
+    PreparedTarget P;
+    P.raw = true;
+    P.rid = rid; P.n_windows = n_windows; P.len = ctx->read_len[rid];
+    P.win_begin.assign(n_windows + 1, 0);
+    P.aln_now.assign(n_ovl, 0);
+    std::vector<uint32_t> first(n_ovl, 0);
+    uint64_t cb = 0;
+    for (uint32_t i = 0; i < n_ovl; i++) {
+        if (ovl[i].tid != rid) return fail_locked(HB_ERR_ARG, "overlap.tid != rid (alignments must be grouped by target)");
+        if (ovl[i].qid >= ctx->n_reads) return fail_locked(HB_ERR_ARG, "overlap.qid out of range");
+        if (!ovl[i].cigar && ovl[i].cigar_len) return fail_locked(HB_ERR_ARG, "null cigar");
+        if (ovl[i].strand > 1) return fail_locked(HB_ERR_ARG, "strand must be 0 or 1");
+        uint32_t wa, we;
+        if (skeleton_for_alignment(ovl[i], W, n_windows, wa, we) != 0)
+            return fail_locked(HB_ERR_INPUT, "malformed alignment (coordinates) for target " + std::to_string(rid));
+        first[i] = wa;
+        P.aln_now[i] = we - wa;
+        if (we > wa) cb += ovl[i].cigar_len;
+        for (uint32_t w = wa; w < we; w++) P.win_begin[w + 1]++;
+    }
+    for (uint32_t w = 0; w < n_windows; w++) P.win_begin[w + 1] += P.win_begin[w];
+    P.cig_bytes = cb;
+    P.ow.resize(P.win_begin[n_windows]);
+    std::vector<uint32_t> fill(P.win_begin.begin(), P.win_begin.end() - 1);
+    for (uint32_t i = 0; i < n_ovl; i++)  // alignment order inside every window = the reference's push order
+        for (uint32_t w = first[i]; w < first[i] + P.aln_now[i]; w++) P.ow[fill[w]++] = DevOW{i, w, 0, 0, 0, 0, 0, 0, 0, 0};
+    return stage_target(ctx, P, ovl, n_ovl);
 }
 
 int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_size, uint32_t n_windows,
@@ -1298,6 +1410,11 @@ int hb_extract_windows(const hb_overlap* ovl, uint32_t n_ovl, uint32_t window_si
     *n_out = (uint32_t)v.size();
     if (out) memcpy(out, v.data(), std::min<size_t>(v.size(), cap) * sizeof(hb_overlap_window));
     return HB_OK;
+}
+
+int hb_window_range(const hb_overlap* ovl, uint32_t window_size, uint32_t n_windows, uint32_t* first_window, uint32_t* end_window) {
+    if (!ovl || !first_window || !end_window || window_size == 0) return HB_ERR_ARG;
+    return skeleton_for_alignment(*ovl, window_size, n_windows, *first_window, *end_window) == 0 ? HB_OK : HB_ERR_INPUT;
 }
 
 int hb_set_launch_targets(hb_ctx* ctx, uint32_t launch_targets) {

@@ -24,17 +24,30 @@ namespace hb {
 //     target/query offsets, apply the indel filter and compute calculate_accuracy.
 //     One warp per overlap-window.
 // ------------------------------------------------------------------------------------
+template <bool RAW>  // RAW: the overlap-window came from the device windowing (windowing_dev.cu) and its ops from the raw-op arrays
 __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
     const int lane = threadIdx.x & 31;
     const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wi >= b.n_ow) return;
-    const DevOW ow = b.ow[wi];
+    DevOW ow = b.ow[wi];
     const DevOverlap ov = b.ovl[ow.ovl];
+    if ((ov.raw_base != RAW_NONE) != RAW) return;
     const DevWin win = b.win[ow.win];
     const uint8_t* __restrict__ cg = b.cig + ov.cig_off + ow.csi;
     const int slen = (int)ow.cei - (int)ow.csi;
     uint32_t flags = 0;
-    if (slen <= 0 || ow.cei > ov.cig_len) flags |= OWF_BAD;
+    uint32_t nops = 0;
+    const uint32_t* __restrict__ rkl = nullptr;
+    if (RAW) {
+        flags = b.ow_flags[wi];  // OWF_BAD from k_parse_cigars / k_windows
+        nops = (flags & OWF_BAD) ? 0u : b.ow_nops[wi];
+        ow.op_base = b.op_base_dev + (uint32_t)b.ow_opoff[wi];
+        if (lane == 0) b.ow_mut[wi].op_base = ow.op_base;
+        rkl = b.raw_kl + ov.raw_base + ow.csi;
+        if (nops == 0) flags |= OWF_BAD;
+    } else {
+        if (slen <= 0 || ow.cei > ov.cig_len) flags |= OWF_BAD;
+    }
     if (ow.tstart < win.tstart || ow.tstart >= win.tstart + win.len) flags |= OWF_BAD;
     // query region must lie inside the query read (decode() asserts, src/haec_io.rs:157)
     {
@@ -46,8 +59,7 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
             if (ov.qend < ow.qend || ov.qend - ow.qstart > qlen) flags |= OWF_BAD;
         }
     }
-    uint32_t nops = 0;
-    if (!(flags & OWF_BAD)) {
+    if (!RAW && !(flags & OWF_BAD)) {
         // ---- parse: lanes 0..9 look back, lanes 10..31 are the 22 active bytes of this step
         for (int base = 0; base < slen; base += 22) {
             const int idx = base - 10 + lane;
@@ -80,7 +92,8 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
                 // outside anything an aligner emits; flag them like the other parse errors.
                 if (kind == 1u || num == 0 || ndig == 0 || ndig >= 10) flags |= OWF_BAD;
                 const uint32_t k = nops + __popc(mask & ((1u << lane) - 1u));
-                b.op_kl[ow.op_base + k] = kind | (num << 2);
+                if (k < (uint32_t)slen / 2u + 1u) b.op_kl[ow.op_base + k] = kind | (num << 2);  // the slice's region holds slen / 2 + 1 ops
+                else flags |= OWF_BAD;  // more letters than digits
             }
             nops += __popc(mask);
         }
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(128) k_tokenize(BatchView b) {
             const uint32_t k = k0 + lane;
             uint32_t kind = 0, raw = 0, eff = 0;
             if (k < nops) {
-                const uint32_t kl = b.op_kl[ow.op_base + k];
+                const uint32_t kl = RAW ? rkl[k] : b.op_kl[ow.op_base + k];
                 kind = kl & 3u;
                 raw = kl >> 2;
                 eff = raw;
@@ -869,6 +882,11 @@ __global__ void __launch_bounds__(256) k_cons_write(BatchView b) {
     }
 }
 
+void launch_scan_u32(const uint32_t* in, uint64_t* out, uint32_t n, uint32_t* counters, int total_slot, uint64_t cap, int overflow_slot,
+                     cudaStream_t st) {
+    k_scan_u32<<<1, 1024, 0, st>>>(in, out, n, counters, total_slot, cap, overflow_slot);
+}
+
 // ------------------------------------------------------------------------------------
 // launch wrappers (called from ctx.cu)
 // ------------------------------------------------------------------------------------
@@ -888,7 +906,13 @@ cudaError_t features_configure(uint32_t W) {
 
 int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt) {
     int n = 0;
-    if (b.n_ow) { kt.begin(K_TOKENIZE); k_tokenize<<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); kt.end(); n++; }
+    if (b.n_ow) {
+        kt.begin(K_TOKENIZE);
+        if (b.n_raw) n += launch_windowing(b, st);  // device extract_windows for the alignments submitted raw
+        if (b.n_raw) { k_tokenize<true><<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); n++; }
+        if (b.n_raw < b.n_ovl) { k_tokenize<false><<<(b.n_ow * 32 + 127) / 128, 128, 0, st>>>(b); n++; }
+        kt.end();
+    }
     kt.begin(K_PASS1); k_pass1<<<b.n_win, 256, pass1_smem(b.W), st>>>(b); kt.end(); n++;
     if (b.n_ovl) { kt.begin(K_SCORES); k_scores<<<(b.n_ovl + 255) / 256, 256, 0, st>>>(b); kt.end(); n++; }
     kt.begin(K_PASS2A); k_pass2a<<<b.n_win, 256, pass2a_smem(b.W), st>>>(b); kt.end(); n++;

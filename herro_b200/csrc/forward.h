@@ -140,6 +140,11 @@ void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]);
 cudaError_t features_configure(uint32_t W);
 int launch_features_a(const BatchView& b, cudaStream_t st, KTimer& kt);
 int launch_pileup(const BatchView& b, cudaStream_t st, KTimer& kt, bool v1);
+// windowing_dev.cu: extract_windows on the device (parse, boundaries, op-slot scan); returns the number of kernels launched
+int launch_windowing(const BatchView& b, cudaStream_t st);
+// k_scan_u32 of features.cu
+void launch_scan_u32(const uint32_t* in, uint64_t* out, uint32_t n, uint32_t* counters, int total_slot, uint64_t cap, int overflow_slot,
+                     cudaStream_t st);
 // pileup.cu
 cudaError_t pileup_configure();
 void launch_pileup_v2(const BatchView& b, cudaStream_t st);

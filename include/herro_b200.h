@@ -103,8 +103,16 @@ int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_ove
 
 /* Same, but the library also performs windowing::extract_windows (src/windowing.rs:44-273)
  * on the raw alignments — for hosts that hand over `(tid, Vec<Alignment>)` straight from
- * alignment_reader (src/overlaps.rs:371-373). */
+ * alignment_reader (src/overlaps.rs:371-373).  The windowing runs ON THE DEVICE: the calling
+ * thread only derives, from the PAF coordinates, which windows each alignment contributes to, and copies the CIGARs;
+ * no CIGAR byte is parsed on the host.  Consequently a malformed CIGAR (or one that does not span its PAF
+ * coordinates) is reported for its target by hb_poll_corrected (HB_ERR_INPUT), not by this call; coordinate errors
+ * (inverted ranges, windows past the end of the target) still fail here. */
 int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint32_t n_ovl);
+
+/* Host-only utility: the windows [*first_window, *end_window) one alignment contributes OverlapWindows to — the
+ * coordinate-only part of extract_windows (src/windowing.rs:53-125,260-272).  HB_ERR_INPUT where the reference panics. */
+int hb_window_range(const hb_overlap* ovl, uint32_t window_size, uint32_t n_windows, uint32_t* first_window, uint32_t* end_window);
 
 /* Host-only utility (no context, no GPU): windowing::extract_windows (src/windowing.rs:44-273) of
  * the n_ovl alignments of one target that has n_windows windows (overlap_idx = position in

@@ -36,32 +36,58 @@ def _drain_all(ctx):
         ok[r.rid] = r.segments
 
 
-def test_malformed_cigar_is_rejected_at_submit_and_does_not_poison_the_context():
-    """hb_submit_alignments runs the windowing on the host: a CIGAR that overruns the target is the reference's
-    panic in extract_windows (src/windowing.rs) -> HB_ERR_INPUT for that call only."""
+@pytest.mark.parametrize("host_windowing", [False, True])
+def test_malformed_cigar_fails_only_its_target(host_windowing, monkeypatch):
+    """A CIGAR that overruns the target is the reference's panic in extract_windows (src/windowing.rs).  hb_submit_alignments
+    windows on the device: the target polls HB_ERR_INPUT, every other target is corrected as usual.  With the host windowing
+    (HERRO_B200_HOST_WINDOWING, the A-B path) the same input is rejected by the submit call itself."""
     from herro_b200.api import HerroError
     rs = helpers.small_readset(n_reads=20, mean_len=6000, seed=21)
     model = helpers.model_path(seed=3)
     good = helpers.run_product(rs, model, 4096, 64)["segments"]
+    if host_windowing:
+        monkeypatch.setenv("HERRO_B200_HOST_WINDOWING", "1")
     ctx = _ctx(rs, model, launch_targets=1 << 20)
     victim = next(t for t in range(rs.n) if rs.aln_off[t + 1] - rs.aln_off[t] >= 2)
-    a0 = int(rs.aln_off[victim])
     bad_cig = np.frombuffer(b"999999M", dtype=np.uint8).copy()
     ovl = _overlaps(rs, victim)
     ovl["cigar"][0] = bad_cig.ctypes.data
     ovl["cigar_len"][0] = len(bad_cig)
-    with pytest.raises(HerroError) as ei:
+    if host_windowing:
+        with pytest.raises(HerroError) as ei:
+            ctx.submit_alignments(victim, ovl)
+        assert ei.value.code == -4  # HB_ERR_INPUT
+    else:
         ctx.submit_alignments(victim, ovl)
-    assert ei.value.code == -4  # HB_ERR_INPUT
     for t in range(rs.n):
         if t != victim and rs.aln_off[t + 1] > rs.aln_off[t]:
             ctx.submit_alignments(t, _overlaps(rs, t))
     ctx.flush()
     ok, bad = _drain_all(ctx)
-    assert not bad
+    assert list(bad.values()) == ([] if host_windowing else [-4])
     for t, segs in ok.items():
         assert (segs or None) == good[t]
     assert victim not in ok
+
+
+@pytest.mark.parametrize("garbage", [b"12M3X4M", b"M", b"12", b"0M", b"5M5", b"99999999999M"])
+def test_unparsable_cigars_fail_only_their_target(garbage):
+    """CigarIter panics on anything but [0-9]+[MID] with non-zero lengths (src/aligners.rs:252-293): reported per target."""
+    rs = helpers.small_readset(n_reads=12, mean_len=6000, seed=27)
+    model = helpers.model_path(seed=3)
+    ctx = _ctx(rs, model, launch_targets=1 << 20)
+    victim = next(t for t in range(rs.n) if rs.aln_off[t + 1] - rs.aln_off[t] >= 2)
+    g = np.frombuffer(garbage, dtype=np.uint8).copy()
+    ovl = _overlaps(rs, victim)
+    ovl["cigar"][1] = g.ctypes.data
+    ovl["cigar_len"][1] = len(g)
+    ctx.submit_alignments(victim, ovl)
+    others = [t for t in range(rs.n) if t != victim and rs.aln_off[t + 1] > rs.aln_off[t]]
+    for t in others:
+        ctx.submit_alignments(t, _overlaps(rs, t))
+    ctx.flush()
+    ok, bad = _drain_all(ctx)
+    assert list(bad.values()) == [-4] and set(ok) == set(others)
 
 
 def test_inconsistent_overlap_window_fails_only_its_target():

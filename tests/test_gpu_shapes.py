@@ -70,6 +70,24 @@ def test_windows_longer_than_one_pileup_chunk():
     helpers.compare({"windows": ora["windows"], "logits": {}, "segments": {}}, {**got, "segments": {}}, None)
 
 
+# ------------------------------------------------------------------------------------------ device windowing A-B
+@pytest.mark.parametrize("profile,W,b,n,ml,cov", [("r10", 4096, 64, 50, 12000, 25.0), ("r9", 1024, 8, 60, 6000, 15.0), ("r10", 512, 4, 60, 5000, 12.0)])
+def test_device_windowing_equals_host_windowing(profile, W, b, n, ml, cov):
+    """hb_submit_alignments windows on the device (windowing_dev.cu: CIGAR parse, boundary search, op-slot scan); with
+    HERRO_B200_HOST_WINDOWING it runs the C++ restatement of extract_windows on the calling thread.  Same matrices, same
+    segments — and both equal the oracle (whose extract_windows is a third implementation)."""
+    rs = helpers.small_readset(n_reads=n, mean_len=ml, seed=71, profile=profile, coverage=cov, min_ovl=max(600, W // 2), sd_frac=0.3)
+    model = helpers.model_path(seed=3)
+    with _env(HERRO_B200_HOST_WINDOWING=1):
+        host = helpers.run_product(rs, model, W, b, keep_debug=True)
+    dev = helpers.run_product(rs, model, W, b, keep_debug=True)
+    assert host["segments"] == dev["segments"]
+    _same_windows(host, dev)
+    assert host["stats"]["overlap_windows"] == dev["stats"]["overlap_windows"]
+    ora = helpers.run_oracle(rs, model, W, b, with_forward=False)
+    helpers.compare({"windows": ora["windows"], "logits": {}, "segments": {}}, {**dev, "segments": {}}, None)
+
+
 # ------------------------------------------------------------------------------------------ benchmark shapes
 def test_cfg2_shape_15kb_40x_b64():
     """BASELINE.json configs[1]: 15 kb reads, R10 profile, 40x, W = 4096, -b 64 — 200 target reads against the oracle."""

@@ -76,3 +76,26 @@ def test_window_invariants(W):
             assert wts + tl == wend, (cigar, wi)
             assert qe - qs == ql
             assert wi * W <= wts < (wi + 1) * W
+
+
+def test_window_range_matches_extract_windows():
+    """hb_window_range (the coordinate-only skeleton the device windowing is laid out from, ctx.cu) names exactly the
+    windows extract_windows emits, for every alignment of synthetic sets at several window sizes."""
+    from herro_b200 import Context, api
+    from tools import synth
+    n_checked = 0
+    for W, seed in ((512, 1), (1024, 2), (4096, 3)):
+        rs = synth.generate(60, 6000 if W < 4096 else 12000, seed=seed, coverage=15.0, min_ovl=max(600, W // 2), sd_frac=0.3)
+        for t in range(rs.n):
+            a0, a1 = int(rs.aln_off[t]), int(rs.aln_off[t + 1])
+            if a1 == a0:
+                continue
+            nw = (int(rs.off[t + 1] - rs.off[t]) + W - 1) // W
+            ovl = Context.make_overlaps(rs.ovl9[a0:a1], rs.cigars, rs.cig_off[a0:a1 + 1])
+            for k in range(a1 - a0):
+                ows = api.extract_windows(ovl[k:k + 1], W, nw)
+                got = sorted(int(x) for x in ows["window_idx"])
+                first, end = api.window_range(ovl[k:k + 1], W, nw)
+                assert got == list(range(first, end)), (W, t, k, got, first, end)
+                n_checked += 1
+    assert n_checked > 1000
