@@ -97,13 +97,14 @@ def load_library():
     L.hb_debug_window_shape.argtypes = [vp, u32, u32, u32p]
     L.hb_debug_dump_window.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp]
     L.hb_replay_last_launch.argtypes = [vp, u32, C.POINTER(C.c_float)]
+    L.hb_dump_features.argtypes = [vp, u32, C.c_char_p, vp]
     fp = C.POINTER(C.c_float)
     L.hb_selftest_gemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, C.c_int, u32, fp, fp, fp, fp]
     _lib = L
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_window_range", "hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_dump_features", "hb_window_range", "hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -328,6 +329,14 @@ class Context:
                                                  sup.ctypes.data, rows.ctypes.data, info.ctypes.data, bl.ctypes.data))
         return dict(L=L, n_alns=n_alns, bases=bases, quals=quals, supported=sup[:ns], sup_rows=rows[:ns],
                     info_logits=info[:ns], bases_logits=bl[:ns])
+
+    def dump_features(self, rid: int, out_dir: str, read_names: list):
+        """`herro features` files of target `rid` (of the most recent launch; keep_debug) under out_dir/<read id>/."""
+        if getattr(self, "_names_src", None) is not read_names:
+            self._names_src = read_names
+            self._names_buf = [n if isinstance(n, bytes) else str(n).encode() for n in read_names]
+            self._names_arr = (C.c_char_p * len(read_names))(*self._names_buf)
+        self._check(self._L.hb_dump_features(self._h, rid, out_dir.encode(), self._names_arr))
 
     def replay_last_launch(self, iters: int = 1) -> float:
         ms = C.c_float()

@@ -107,6 +107,8 @@ struct BatchView {
     const double* ln_table;  // ln(k) computed by the host libm, k < ln_table_n
     uint32_t ln_table_n;
     // per window, pass 2
+    uint32_t* rank_ow;  // [n_ow] every surviving overlap-window of the window in final rank order (CSR with win.ow_begin): the
+                        // `ids` of FeaturesOutput::update (src/features.rs:569), needed only by the feature dump
     uint32_t* sel_ow;   // [n_win * 30]
     uint32_t* w_nsel;   // n_alns
     uint32_t* rowmap;   // [n_win * (W+1)]: row'(p), last = L'

@@ -23,6 +23,7 @@
 
 #include <pthread.h>
 #include <sched.h>
+#include <sys/stat.h>
 
 #include "../../include/herro_b200.h"
 #include "common.cuh"
@@ -198,6 +199,7 @@ struct LastLaunch {  // host copies of per-window metadata of the most recent la
     std::vector<DevWin> win;
     std::vector<uint32_t> w_L, w_nsel, w_nsup;
     std::vector<uint64_t> w_rowbase, w_supbase;
+    std::vector<uint32_t> ow_qid;  // KEEP_DEBUG: query read of every overlap-window (feature dump)
     std::unordered_map<uint64_t, uint32_t> index;  // (rid << 32 | wid) -> window
     uint64_t n_sup = 0, total_rows = 0;
     BatchView view;
@@ -241,18 +243,19 @@ struct hb_ctx {
         DevBuf d_mat_b, d_mat_q, d_row_emit, d_sup_row, d_sup_pk, d_w_supbase, d_fwd_win, d_fwd_row;
         DevBuf d_w_outlen, d_w_outoff, d_out, d_tgt_err, d_counters, d_ws, d_logits, d_info, d_big_key, d_big_cand, d_big_score;
         DevBuf d_raw_kl, d_raw_t, d_raw_q, d_aln_nops, d_aln_flags, d_ow_opoff;  // device windowing (windowing_dev.cu)
+        DevBuf d_rank_ow;
         uint64_t rows_cap = 0;
         uint64_t seen_sizes = 0;  // version of hb_ctx::lane_sizes this lane has been pre-sized to
         LastLaunch last;
         std::thread worker;
-        static constexpr int N_DEV = 50;
+        static constexpr int N_DEV = 51;
         void all_bufs(DevBuf* (&out)[N_DEV]) {
             DevBuf* bufs[N_DEV] = {&d_tgt, &d_win, &d_ovl, &d_ow, &d_cig, &d_op_kl, &d_op_t, &d_op_q, &d_ow_nops, &d_ow_flags, &d_ow_acc,
                                    &d_ow_tend, &d_col_ow, &d_w_n1, &d_w_S, &d_ovl_n, &d_ovl_tot, &d_ovl_score, &d_sel_ow, &d_w_nsel,
                                    &d_rowmap, &d_w_L, &d_w_rowbase, &d_w_nsup, &d_w_reflmax, &d_mat_b, &d_mat_q, &d_row_emit, &d_sup_row,
                                    &d_sup_pk, &d_w_supbase, &d_fwd_win, &d_fwd_row, &d_w_outlen, &d_w_outoff, &d_out, &d_tgt_err,
                                    &d_counters, &d_ws, &d_logits, &d_info, &d_big_key, &d_big_cand, &d_big_score,
-                                   &d_raw_kl, &d_raw_t, &d_raw_q, &d_aln_nops, &d_aln_flags, &d_ow_opoff};
+                                   &d_raw_kl, &d_raw_t, &d_raw_q, &d_aln_nops, &d_aln_flags, &d_ow_opoff, &d_rank_ow};
             for (int i = 0; i < N_DEV; i++) out[i] = bufs[i];
         }
         void bind_stream() { DevBuf* bufs[N_DEV]; all_bufs(bufs); for (DevBuf* b : bufs) b->st = stream; }
@@ -548,6 +551,7 @@ int ensure_batch_buffers(hb_ctx* ctx, hb_ctx::Lane* L, const HostBatch& hbt) {
     CK(L->d_big_cand.ensure(ow1 * 4));
     CK(L->d_big_score.ensure(ow1 * 8));
     CK(L->d_ow_opoff.ensure(ow1 * 8));
+    CK(L->d_rank_ow.ensure(ow1 * 4));
     CK(L->d_w_n1.ensure(nw * 4));
     CK(L->d_w_S.ensure(nw * 4));
     const size_t no1 = std::max<size_t>(no, 1);
@@ -616,6 +620,7 @@ void set_view_ptrs(hb_ctx* ctx, hb_ctx::Lane* L, BatchView& b) {
     b.ovl_score = L->d_ovl_score.as<double>();
     b.ln_table = ctx->d_ln.as<double>();
     b.ln_table_n = ctx->ln_n;
+    b.rank_ow = L->d_rank_ow.as<uint32_t>();
     b.sel_ow = L->d_sel_ow.as<uint32_t>();
     b.w_nsel = L->d_w_nsel.as<uint32_t>();
     b.rowmap = L->d_rowmap.as<uint32_t>();
@@ -855,6 +860,10 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
         ll.w_rowbase[w] = rb; rb += h_L[w];
         ll.w_supbase[w] = sb; sb += h_nsup[w];
         if (ctx->opt.flags & HB_FLAG_KEEP_DEBUG) ll.index[((uint64_t)hbt.win[w].rid << 32) | hbt.win[w].wid] = (uint32_t)w;
+    }
+    if (ctx->opt.flags & HB_FLAG_KEEP_DEBUG) {
+        ll.ow_qid.resize(hbt.ow.size());
+        for (size_t i = 0; i < hbt.ow.size(); i++) ll.ow_qid[i] = hbt.ovl[hbt.ow[i].ovl].qid;
     }
     ll.n_sup = n_sup;
     ll.total_rows = total_rows;
@@ -1565,6 +1574,94 @@ int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases
         if (sup_rows) CK(cudaMemcpy(sup_rows, ll.view.sup_row + rb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
         if (info_logits) CK(cudaMemcpy(info_logits, lane->d_info.as<float>() + sb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
         if (bases_logits) CK(cudaMemcpy(bases_logits, lane->d_logits.as<float>() + sb * 5, (size_t)ns * 20, cudaMemcpyDeviceToHost));
+    }
+    return HB_OK;
+}
+
+// ---- `herro features` dump (src/features.rs:724-764,806-839) ---------------------------------------------------------
+// .npy v1.0 exactly as numpy writes it: magic, u16 header length, the dict, padded with spaces to a multiple of 64, '\n'.
+static bool write_npy(const std::string& path, const std::string& descr, const std::string& shape, const void* data, size_t bytes) {
+    std::string dict = "{'descr': " + descr + ", 'fortran_order': False, 'shape': " + shape + ", }";
+    size_t total = 10 + dict.size() + 1;
+    const size_t pad = (64 - total % 64) % 64;
+    dict.append(pad, ' ');
+    dict.push_back('\n');
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const unsigned char magic[8] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+    const uint16_t hl = (uint16_t)dict.size();
+    bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&hl, 2, 1, f) == 1 && fwrite(dict.data(), 1, dict.size(), f) == dict.size() &&
+              (bytes == 0 || fwrite(data, 1, bytes, f) == bytes);
+    ok = fclose(f) == 0 && ok;
+    return ok;
+}
+
+int hb_dump_features(hb_ctx* ctx, uint32_t rid, const char* out_dir, const char* const* read_names) {
+    if (!ctx || !out_dir || !read_names) return HB_ERR_ARG;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cv_idle.wait(lk, [&] { return ctx->idle(); });
+    CK(cudaSetDevice(ctx->device));
+    if (rid >= ctx->n_reads || !read_names[rid]) return fail(ctx, HB_ERR_ARG, "rid out of range / unnamed read");
+    uint32_t w0;
+    int rc = find_window(ctx, rid, 0, &w0);
+    if (rc) return rc;
+    hb_ctx::Lane* lane = &ctx->lanes[ctx->last_lane];
+    const LastLaunch& ll = lane->last;
+    const uint32_t W = ctx->opt.window_size, n_windows = (ctx->read_len[rid] + W - 1) / W;
+    const std::string dir = std::string(out_dir) + "/" + read_names[rid];
+    {   // create_dir_all
+        std::string acc;
+        for (size_t i = 0; i <= dir.size(); i++) {
+            if (i == dir.size() || dir[i] == '/') { if (!acc.empty()) mkdir(acc.c_str(), 0777); }
+            if (i < dir.size()) acc.push_back(dir[i]);
+        }
+    }
+    static const char ASCII[13] = "ACGT*acgt#..";  // BASES_MAP inverted (src/inference.rs:23-31)
+    std::vector<uint8_t> tb, tq, feat;
+    std::vector<uint32_t> pk, order;
+    for (uint32_t wid = 0; wid < n_windows; wid++) {
+        const uint32_t w = w0 + wid;
+        if (w >= ll.win.size() || ll.win[w].rid != rid || ll.win[w].wid != wid) return fail(ctx, HB_ERR_STATE, "target is not whole in the most recent launch");
+        const uint32_t L = ll.w_L[w], ns = ll.w_nsup[w];
+        const uint64_t rb = ll.w_rowbase[w];
+        tb.resize((size_t)L * ROW_BYTES); tq.resize((size_t)L * ROW_BYTES);
+        if (L) {
+            CK(cudaMemcpy(tb.data(), ll.view.mat_bases + rb * ROW_BYTES, tb.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(tq.data(), ll.view.mat_quals + rb * ROW_BYTES, tq.size(), cudaMemcpyDeviceToHost));
+        }
+        // features: [2, L', 31] u8 — plane 0 the ASCII bases, plane 1 the quality bytes
+        feat.resize((size_t)2 * L * R_COLS);
+        for (uint32_t r = 0; r < L; r++)
+            for (int c = 0; c < R_COLS; c++) {
+                feat[(size_t)r * R_COLS + c] = (uint8_t)ASCII[tb[(size_t)r * ROW_BYTES + c] < 12 ? tb[(size_t)r * ROW_BYTES + c] : 11];
+                feat[(size_t)L * R_COLS + (size_t)r * R_COLS + c] = tq[(size_t)r * ROW_BYTES + c];
+            }
+        const std::string base = dir + "/" + std::to_string(wid);
+        if (!write_npy(base + ".features.npy", "'|u1'", "(2, " + std::to_string(L) + ", " + std::to_string(R_COLS) + ")", feat.data(), feat.size()))
+            return fail(ctx, HB_ERR_ARG, "cannot write " + base + ".features.npy");
+        // supported: 1-D array of SupportedPos {pos: u16, ins: u8}, packed (3 bytes per record)
+        pk.resize(ns);
+        if (ns) CK(cudaMemcpy(pk.data(), ll.view.sup_pk + rb, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> rec((size_t)ns * 3);
+        for (uint32_t k = 0; k < ns; k++) {
+            const uint16_t pos = (uint16_t)(pk[k] >> 8);
+            memcpy(&rec[(size_t)k * 3], &pos, 2);
+            rec[(size_t)k * 3 + 2] = (uint8_t)(pk[k] & 0xffu);
+        }
+        if (!write_npy(base + ".supported.npy", "[('pos', '<u2'), ('ins', '|u1')]", "(" + std::to_string(ns) + ",)", rec.data(), rec.size()))
+            return fail(ctx, HB_ERR_ARG, "cannot write " + base + ".supported.npy");
+        // ids: the query reads of ALL surviving overlaps of the window in final rank order (src/features.rs:569)
+        uint32_t n1 = 0;
+        CK(cudaMemcpy(&n1, ll.view.w_n1 + w, 4, cudaMemcpyDeviceToHost));
+        order.resize(n1);
+        if (n1) CK(cudaMemcpy(order.data(), ll.view.rank_ow + ll.win[w].ow_begin, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
+        FILE* f = fopen((base + ".ids.txt").c_str(), "wb");
+        if (!f) return fail(ctx, HB_ERR_ARG, "cannot write " + base + ".ids.txt");
+        for (uint32_t k = 0; k < n1; k++) {
+            const uint32_t q = order[k] < ll.ow_qid.size() ? ll.ow_qid[order[k]] : 0;
+            fprintf(f, "%s\n", q < ctx->n_reads && read_names[q] ? read_names[q] : "?");
+        }
+        fclose(f);
     }
     return HB_OK;
 }

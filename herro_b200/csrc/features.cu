@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(256) k_pass2a(BatchView b) {
             const double sj = sc[j];
             r += (sj > si || (sj == si && j < i)) ? 1u : 0u;
         }
+        b.rank_ow[win.ow_begin + r] = b.col_ow[win.ow_begin + i];
         if (r < (uint32_t)TOP_K) {
             s_sel[r] = b.col_ow[win.ow_begin + i];
             b.sel_ow[w * TOP_K + r] = s_sel[r];

@@ -193,6 +193,15 @@ int hb_debug_window_shape(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint32_t* sha
 int hb_debug_dump_window(hb_ctx* ctx, uint32_t rid, uint32_t wid, uint8_t* bases, uint8_t* quals,
                          uint32_t* supported, uint32_t* sup_rows, float* info_logits, float* bases_logits);
 
+/* `herro features` (src/lib.rs:50-111, src/features.rs:724-764,806-839) from the device path: for target `rid` of the
+ * most recent launch (HB_FLAG_KEEP_DEBUG) writes, per window, under <out_dir>/<read_names[rid]>/ :
+ *   <wid>.features.npy   u8 [2, L', 31]: plane 0 the pileup as raw ASCII (ACGT / acgt / '*' '#' / '.'), plane 1 the qualities
+ *   <wid>.supported.npy  1-D records {pos: u16, ins: u8}  (SupportedPos, src/features.rs:894-898)
+ *   <wid>.ids.txt        the query read ids of all overlaps that survived the filter, in final rank order (src/features.rs:569)
+ * i.e. the arguments of FeaturesOutput::update.  read_names[i] = id of read i (NUL-terminated), n_reads entries.
+ * The .npy headers are the ones numpy writes (v1.0, padded to 64 bytes). */
+int hb_dump_features(hb_ctx* ctx, uint32_t rid, const char* out_dir, const char* const* read_names);
+
 /* ---- device-resident replay, used by bench.py for the HBM-resident `value` -------------- */
 /* Re-run all device stages of the most recent launch from its inputs already in HBM
  * (no host<->device copies), `iters` times; returns the CUDA-event milliseconds in *ms. */

@@ -238,3 +238,34 @@ def test_shard_invariance_of_the_corrected_set(world):
         sizes.append(len(mine))
     assert union == whole
     assert sum(sizes) == rs.n
+
+
+# ------------------------------------------------------------------------------------------ `herro features` dump
+def test_feature_dump_matches_golden_files(tmp_path):
+    """hb_dump_features writes the reference's `herro features` files (src/features.rs:724-764): [2,L',31] ASCII pileup +
+    qualities, SupportedPos records, ranked query ids.  tests/golden/features_dump/ holds the same files produced by the CPU
+    oracle through numpy (tools/make_feature_fixture.py): byte-identical, headers included."""
+    import glob
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_feature_fixture", os.path.join(sys_path_root, "tools", "make_feature_fixture.py"))
+    fx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fx)
+    rs = fx.readset()
+    model = helpers.model_path(seed=3)
+    got = helpers.run_product(rs, model, fx.W, 4, targets=list(fx.TARGETS), keep_debug=True, dump=False)
+    ctx = got["ctx"]
+    for t in fx.TARGETS:
+        ctx.dump_features(t, str(tmp_path), rs.ids)
+    golden = os.path.join(sys_path_root, "tests", "golden", "features_dump")
+    n = 0
+    for t in fx.TARGETS:
+        want = sorted(glob.glob(os.path.join(golden, rs.ids[t], "*")))
+        have = sorted(glob.glob(os.path.join(str(tmp_path), rs.ids[t], "*")))
+        assert [os.path.basename(p) for p in want] == [os.path.basename(p) for p in have] and want
+        for a, b in zip(want, have):
+            assert open(a, "rb").read() == open(b, "rb").read(), os.path.basename(a)
+            n += 1
+    assert n >= 30
+    f = np.load(os.path.join(str(tmp_path), rs.ids[0], "0.features.npy"))
+    assert f.dtype == np.uint8 and f.shape[0] == 2 and f.shape[2] == 31 and set(np.unique(f[0])) <= set(b"ACGTacgt*#.")
