@@ -1,131 +1,69 @@
-"""`python -m herro_b200.cli inference ...` — the reference's `herro inference` command line
-(src/main.rs:64-112, README.md:75-96) on top of the C ABI, for plumbing runs (BASELINE.json configs[0]):
+"""`python -m herro_b200.cli {inference,features} ...` — the reference's two sub-commands (src/main.rs:10-112, README.md:75-96)
+as a thin argument parser over the native host pipeline (herro_b200/host/io.cpp -> the C ABI of libherro_b200):
 
     python -m herro_b200.cli inference --read-alns <dir> -t 4 -d 0 -m model.hbw -b 64 reads.fastq out.fasta
+    python -m herro_b200.cli features  --read-alns <dir> -m model.hbw reads.fastq out_dir
 
-Host data plane in Python (FASTQ, `*.oec.zst` batches via pyarrow's zstd, FASTA writer): in deployment
-that part is the unchanged Rust binary.  Semantics kept from the reference: reads shorter
-than `-w` are not loaded (src/haec_io.rs:48), unknown names / self overlaps / repeated (query,target) pairs
-are skipped (src/overlaps.rs:137-185), `-c` cluster files restrict targets to core reads (:154-159).
+Nothing is computed here: FASTQ parsing / 2-bit packing, `*.oec.zst` decoding and PAF parsing, the feature / consumer threads
+and the FASTA writer are C++ threads (hbh_inference); `features` drives hb_dump_features launch by launch.  In deployment this
+role is played by the unchanged Rust binary; the flags keep the reference's meaning: reads shorter than `-w`
+are not loaded (src/haec_io.rs:48), unknown names / self overlaps / repeated (query,target) pairs are skipped
+(src/overlaps.rs:137-185), `-c` cluster files restrict targets to core reads (:154-159).
 """
 from __future__ import annotations
 
 import argparse
-import glob
-import gzip
-import os
 import sys
 
-import numpy as np
-
-from . import api
-
-
-def read_fastq(path, min_len):
-    """-> ids, descriptions, seqs(list[bytes]), quals(list[bytes]) — get_reads (src/haec_io.rs:37-75)."""
-    op = gzip.open if path.endswith(".gz") else open
-    ids, descs, seqs, quals = [], [], [], []
-    with op(path, "rb") as f:
-        while True:
-            h = f.readline()
-            if not h:
-                break
-            s = f.readline().rstrip(b"\r\n")
-            f.readline()
-            q = f.readline().rstrip(b"\r\n")
-            if len(s) < min_len:
-                continue
-            hdr = h[1:].rstrip(b"\r\n")
-            cut = min([i for i in (hdr.find(b" "), hdr.find(b"\t")) if i >= 0], default=-1)
-            ids.append(hdr if cut < 0 else hdr[:cut])
-            descs.append(None if cut < 0 else hdr[cut + 1:])
-            seqs.append(s)
-            quals.append(q)
-    return ids, descs, seqs, quals
+from . import api, hostio
 
 
 def read_cluster(path):
-    core, neigh = set(), set()
+    """src/lib.rs:208-239: `0\\t<id>` core, `1\\t<id>` neighbour."""
+    core, neigh = [], []
     for line in open(path, "rb"):
         f = line.rstrip(b"\n").split(b"\t")
-        (core if f[0] == b"0" else neigh).add(f[1])
+        if f[0] == b"0":
+            core.append(f[1])
+        elif f[0] == b"1":
+            neigh.append(f[1])
+        else:
+            raise SystemExit("Invalid cluster file")
     return core, neigh
-
-
-def read_oec_batches(alns_dir, name_to_id, core=None):
-    """parse_paf over every `*.oec.zst` (src/overlaps.rs:117-202,288-323) -> {tid: [(ovl9, cigar)]}"""
-    import pyarrow as pa
-    codec = pa.Codec("zstd")
-    out = {}
-    for p in sorted(glob.glob(os.path.join(alns_dir, "*.oec.zst"))):
-        raw = open(p, "rb").read()
-        # single-frame streams written without a content size are handled by the streaming reader
-        try:
-            data = pa.CompressedInputStream(pa.BufferReader(raw), "zstd").read()
-        except Exception:
-            data = codec.decompress(raw, asbytes=True)
-        lines = data.split(b"\n")
-        n_targets = int(lines[0])
-        seen = set()
-        for line in lines[1 + n_targets:]:
-            if not line:
-                continue
-            f = line.split(b"\t")
-            qid = name_to_id.get(f[0])
-            if qid is None:
-                continue
-            if core is not None and f[5] not in core:
-                continue
-            tid = name_to_id.get(f[5])
-            if tid is None or tid == qid or (qid, tid) in seen:
-                continue
-            seen.add((qid, tid))
-            ovl = [qid, int(f[1]), int(f[2]), int(f[3]), 0 if f[4][:1] == b"+" else 1, tid, int(f[6]), int(f[7]), int(f[8])]
-            out.setdefault(tid, []).append((ovl, f[-1][5:]))
-    return out
 
 
 def inference(args):
     core = neigh = None
     if args.cluster:
         core, neigh = read_cluster(args.cluster)
-    files = [args.reads] if os.path.isfile(args.reads) else sorted(
-        p for p in glob.glob(os.path.join(args.reads, "*")) if p.endswith(".fastq") or p.endswith(".fastq.gz"))
-    ids, descs, seqs, quals = [], [], [], []
-    for p in files:
-        a, b, c, d = read_fastq(p, args.window_size)
-        for i in range(len(a)):
-            if core is not None and a[i] not in core and a[i] not in neigh:
-                continue
-            ids.append(a[i]); descs.append(b[i]); seqs.append(c[i]); quals.append(d[i])
-    name_to_id = {n: i for i, n in enumerate(ids)}
-    alns = read_oec_batches(args.read_alns, name_to_id, core)
-    off = np.zeros(len(ids) + 1, dtype=np.uint64)
-    off[1:] = np.cumsum([len(s) for s in seqs])
-    seq_arr = np.frombuffer(b"".join(seqs), dtype=np.uint8)
-    qual_arr = np.frombuffer(b"".join(quals), dtype=np.uint8)
     devices = [int(d) for d in str(args.devices).split(",")]
-    ctxs = [api.Context(args.model, d, args.window_size, args.batch_size) for d in devices]
-    for c in ctxs:
-        c.upload_reads(seq_arr, qual_arr, off)
-    # targets are dealt to the devices like the reference's per-device workers pulling one channel
-    n_rec = 0
-    with open(args.output, "wb") as out:
-        for k, (tid, lst) in enumerate(alns.items()):
-            ovl9 = np.array([o for o, _ in lst], dtype=np.uint32)
-            cig = np.frombuffer(b"".join(c for _, c in lst), dtype=np.uint8)
-            coff = np.zeros(len(lst) + 1, dtype=np.uint64)
-            coff[1:] = np.cumsum([len(c) for _, c in lst])
-            ctxs[k % len(ctxs)].submit_alignments(tid, api.Context.make_overlaps(ovl9, cig, coff))
-        for c in ctxs:
-            c.flush()
-            for r in c.drain(skip_failed=True):
-                if r.segments:
-                    out.write(api.fasta_records(ids[r.rid], descs[r.rid], r.segments))
-                    n_rec += len(r.segments)
-            for rid, code, msg in c.failed:  # the reference would have aborted the whole run here; log the read and go on
-                print(f"skipped read {ids[rid].decode() if rid is not None else '?'}: {msg}", file=sys.stderr)
-    print(f"Processed {len(alns)} reads, wrote {n_rec} records.", file=sys.stderr)
+    r = hostio.inference(args.reads, args.read_alns, args.model, args.output, args.window_size, args.batch_size,
+                         args.feat_gen_threads, devices, core, neigh)
+    print(f"Processed {r['targets']} reads, wrote {r['records']} records ({r['corrected_bases']} bases); "
+          f"fastq {r['fastq_load_s'] + r['pack_s']:.2f}s, alignments {r['alignment_ingest_s']:.2f}s, upload {r['read_store_upload_s']:.2f}s, "
+          f"correction {r['correction_s']:.2f}s" + (f"; skipped {r['failed_targets']} reads" if r["failed_targets"] else ""), file=sys.stderr)
+    return r
+
+
+def features(args):
+    """`herro features` (src/lib.rs:50-111): the per-window feature files of every target, from the device path."""
+    R = hostio.Reads(args.reads, min_len=args.window_size)
+    A = hostio.Alignments(args.read_alns, R)
+    ctx = api.Context(args.model, 0, args.window_size, 64, launch_targets=1 << 20, keep_debug=True)
+    R.upload(ctx)
+    n = 0
+    step = max(1, args.targets_per_launch)
+    for k0 in range(0, A.n_targets, step):  # the debug taps keep one launch: dump launch by launch
+        group = range(k0, min(k0 + step, A.n_targets))
+        for k in group:
+            rid, ov = A.target(k)
+            ctx.submit_alignments(rid, ov)
+        ctx.flush()
+        ctx.drain(skip_failed=True)
+        for k in group:
+            ctx.dump_features(int(A.target_rids[k]), args.output, R.ids)
+            n += 1
+    print(f"Wrote the feature files of {n} reads under {args.output}.", file=sys.stderr)
 
 
 def main(argv=None):
@@ -141,9 +79,17 @@ def main(argv=None):
     inf.add_argument("-c", dest="cluster", default="")
     inf.add_argument("reads")
     inf.add_argument("output")
+    ft = sub.add_parser("features")
+    ft.add_argument("--read-alns", required=True)
+    ft.add_argument("-w", dest="window_size", type=int, default=4096)
+    ft.add_argument("-m", dest="model", required=True, help="weights (a context needs them; the feature files do not depend on them)")
+    ft.add_argument("--targets-per-launch", type=int, default=256)
+    ft.add_argument("reads")
+    ft.add_argument("output")
     args = ap.parse_args(argv)
     if args.cmd == "inference":
-        inference(args)
+        return inference(args)
+    return features(args)
 
 
 if __name__ == "__main__":

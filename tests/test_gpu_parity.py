@@ -150,3 +150,41 @@ def test_fused_ffn_and_layernorm_equal_unfused(monkeypatch, env):
         wb = b["windows"][key]
         worst = max(worst, float(np.abs(wa["bases_logits"] - wb["bases_logits"]).max(initial=0.0)))
     assert worst <= 1e-4, worst
+
+
+def test_cli_features_reproduces_the_golden_dump(tmp_path):
+    """`herro features` end to end (FASTQ + *.oec.zst -> per-window feature files) from the inputs committed with the fixture:
+    native ingest (host/io.cpp), device windowing, pileup, hb_dump_features — byte-identical to the oracle-generated files."""
+    import glob
+    import os
+    from herro_b200 import cli
+    golden = os.path.join(helpers.ROOT, "tests", "golden", "features_dump")
+    model = helpers.model_path(seed=3)
+    out = str(tmp_path / "feats")
+    cli.main(["features", "--read-alns", os.path.join(golden, "alns"), "-w", "256", "-m", model, "--targets-per-launch", "5",
+              os.path.join(golden, "reads.fastq"), out])
+    n = 0
+    for d in sorted(glob.glob(os.path.join(golden, "read_*"))):
+        for a in sorted(glob.glob(os.path.join(d, "*"))):
+            b = os.path.join(out, os.path.basename(d), os.path.basename(a))
+            assert open(a, "rb").read() == open(b, "rb").read(), b
+            n += 1
+    assert n >= 30
+
+
+def test_native_pipeline_multithreaded_equals_single_threaded(tmp_path):
+    """hbh_inference with `-t 4` (feature threads racing for targets, results in completion order) writes the same record set."""
+    from herro_b200 import cli
+    from tools import synth
+    rs = helpers.small_readset(n_reads=40, mean_len=7000, seed=14, min_len=4200)
+    fq = str(tmp_path / "reads.fastq")
+    synth.write_fastq(rs, fq)
+    synth.write_oec_batches(rs, str(tmp_path / "alns"), batch_size=7)
+    model = helpers.model_path(seed=3)
+    outs = []
+    for t in ("1", "4"):
+        out = str(tmp_path / f"out{t}.fasta")
+        r = cli.main(["inference", "--read-alns", str(tmp_path / "alns"), "-m", model, "-b", "64", "-t", t, fq, out])
+        assert r["failed_targets"] == 0 and r["records"] > 0
+        outs.append(sorted(open(out, "rb").read().split(b">")[1:]))
+    assert outs[0] == outs[1]
