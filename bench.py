@@ -354,7 +354,7 @@ def main():
     # is the launch the HBM-resident replay re-runs
     ctx.reset_stats()
     ctx.set_kernel_timing(True)
-    harness.run(cut[n_steps - 1], cut[n_steps], 1, None)
+    harness.run(cut[n_steps - 1], cut[n_steps], 1, harness.windowing(cut[n_steps - 1], cut[n_steps], wthr))  # same entry as `e2e`
     st_full = ctx.stats()
     # ---- region 2: device stages only, inputs resident in HBM (one launch's working set is GBs of matrices + activations,
     #      larger than the 126 MB L2, so no L2 flush is needed)

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
     uint32_t* ins = TI + 32 * P_CW;                     // [P_CW] toggles -> rows that are insertion slots (not base rows)
     uint16_t* pref = (uint16_t*)(ins + P_CW);           // [32][P_CW] consumed bases of the column before each word (chunk-local)
     uint16_t* bpref = pref + 32 * P_CW;                 // [P_CW] base rows before each word (chunk-local)
-    ColA* colA = (ColA*)(bpref + P_CW);                 // [32]
+    uint32_t* supbits = (uint32_t*)(bpref + P_CW);      // [P_CW] rows of the chunk that are supported (second get_supported)
+    ColA* colA = (ColA*)(supbits + P_CW);               // [32]
     ColB* colB = (ColB*)(colA + 32);
     ColC* colC = (ColC*)(colB + 32);
     uint32_t* sel_s = (uint32_t*)(colC + 32);           // [16]
@@ -369,26 +370,47 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
                 const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
                 b.row_emit[rowbase + c0 + rl] = (uint8_t)(emit | (sup ? 0x80u : 0u));
             }
-            // ---- ordered list of supported rows: (row, pos << 8 | ins) appended in row order (= thread order)
+            // supported rows are only flagged here (a warp's 32 lanes are 32 consecutive rows = one word of the bitmap);
+            // the ordered list is built once per chunk below, so this loop has no block-wide barrier
             {
                 const uint32_t bal = __ballot_sync(HB_FULL, sup);
-                if (lane == 0) s_warp[warp] = __popc(bal);
-                __syncthreads();
-                if (sup) {
-                    uint32_t off = s_nsup + __popc(bal & ((1u << lane) - 1u));
-                    for (int k = 0; k < warp; k++) off += s_warp[k];
-                    const uint32_t basew = ~ins[wi];  // base rows at or before this row give the target position
-                    const uint32_t upto = (rl & 31u) == 31u ? basew : (basew & ((2u << (rl & 31u)) - 1u));
-                    const uint32_t p = s_pcarry + (uint32_t)bpref[wi] + __popc(upto) - 1u;
+                if (lane == 0 && (g0 >> 3) + (uint32_t)warp < cw) supbits[(g0 >> 3) + warp] = bal;
+            }
+        }
+        __syncthreads();
+        // ---- ordered list of supported rows of the chunk: (row, pos << 8 | ins), appended in row order
+        if (warp == 0) {
+            uint32_t cnt[P_WPL], sum = 0;
+#pragma unroll
+            for (int i = 0; i < P_WPL; i++) {
+                const uint32_t j = lane * P_WPL + i;
+                cnt[i] = sum;
+                sum += j < cw ? __popc(supbits[j]) : 0u;
+            }
+            const uint32_t inc = warp_incl_scan(sum, lane);
+#pragma unroll
+            for (int i = 0; i < P_WPL; i++) {
+                const uint32_t j = lane * P_WPL + i;
+                if (j >= cw) continue;
+                uint32_t bits = supbits[j];
+                uint32_t off = s_nsup + inc - sum + cnt[i];
+                const uint32_t basew = ~ins[j];
+                while (bits) {
+                    const uint32_t bi = (uint32_t)__ffs((int)bits) - 1u;
+                    bits &= bits - 1u;
+                    const uint32_t rl = j * 32u + bi;  // chunk-local row; base rows at or before it give the target position
+                    const uint32_t upto = bi == 31u ? basew : (basew & ((2u << bi) - 1u));
+                    const uint32_t p = s_pcarry + (uint32_t)bpref[j] + __popc(upto) - 1u;
                     const uint32_t kk = (c0 + rl) - rm[p];
                     b.sup_row[rowbase + off] = c0 + rl;
                     b.sup_pk[rowbase + off] = (p << 8) | (kk & 0xffu);  // SupportedPos.ins is a u8 (H13)
+                    off++;
                 }
-                __syncthreads();
-                if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_nsup += t; }
-                __syncthreads();
             }
+            __syncwarp();
+            if (lane == 31) s_nsup += inc;
         }
+        __syncthreads();
         // ---- carry the per-column consumed-base counts and the base-row count into the next chunk
         if (tid < 32) s_carry[tid] += s_tot[tid];
         if (tid == 32) s_pcarry += s_tot[32];
@@ -398,7 +420,8 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
 }
 
 size_t pileup_smem() {
-    return (size_t)2 * 32 * P_CW * 4 + (size_t)P_CW * 4 + (size_t)32 * P_CW * 2 + (size_t)P_CW * 2 + 32 * (sizeof(ColA) + sizeof(ColB) + sizeof(ColC)) +
+    return (size_t)2 * 32 * P_CW * 4 + (size_t)P_CW * 4 + (size_t)32 * P_CW * 2 + (size_t)P_CW * 2 + (size_t)P_CW * 4 +
+           32 * (sizeof(ColA) + sizeof(ColB) + sizeof(ColC)) +
            (16 + 256) * 4 + 64;
 }
 

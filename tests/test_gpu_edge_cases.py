@@ -75,12 +75,19 @@ def test_unparsable_cigars_fail_only_their_target(garbage):
     """CigarIter panics on anything but [0-9]+[MID] with non-zero lengths (src/aligners.rs:252-293): reported per target."""
     rs = helpers.small_readset(n_reads=12, mean_len=6000, seed=27)
     model = helpers.model_path(seed=3)
+    from herro_b200 import api
     ctx = _ctx(rs, model, launch_targets=1 << 20)
-    victim = next(t for t in range(rs.n) if rs.aln_off[t + 1] - rs.aln_off[t] >= 2)
+
+    def windowed(t):  # alignments of t that contribute to a window: only their CIGARs are ever parsed (src/windowing.rs:53-57)
+        ovl = _overlaps(rs, t)
+        nw = (int(rs.off[t + 1] - rs.off[t]) + 4095) // 4096
+        return [k for k in range(len(ovl)) if (lambda r: r[1] > r[0])(api.window_range(ovl[k:k + 1], 4096, nw))]
+    victim = next(t for t in range(rs.n) if len(windowed(t)) >= 2)
     g = np.frombuffer(garbage, dtype=np.uint8).copy()
     ovl = _overlaps(rs, victim)
-    ovl["cigar"][1] = g.ctypes.data
-    ovl["cigar_len"][1] = len(g)
+    k = windowed(victim)[1]
+    ovl["cigar"][k] = g.ctypes.data
+    ovl["cigar_len"][k] = len(g)
     ctx.submit_alignments(victim, ovl)
     others = [t for t in range(rs.n) if t != victim and rs.aln_off[t + 1] > rs.aln_off[t]]
     for t in others:

@@ -90,3 +90,45 @@ def test_gloo_world2_reduction():
     assert res[0][1] == res[1][1] == 2.0          # max over ranks
     assert res[0][2] == res[1][2] == 100.0        # all units accounted for exactly once
     assert res[0][3] + res[1][3] == 100
+
+
+def _shard_worker(rank, world, port, q):
+    """What a rank of `bench.py --gpus N` does on the host: same read set everywhere (deterministic generator), alignments only
+    for its own read-id shard, one all_gather of the per-rank totals (gloo here, nccl on the box)."""
+    import torch
+    import torch.distributed as dist
+    from tools import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = synth.Generator(120, 6000, seed=5, coverage=15.0, min_ovl=1200, threads=2)
+    lens = g.read_lens()
+    n_job = 100
+    mine = shard.shard_targets(lens[:n_job], 4096, rank, world)
+    lo, hi = int(mine[0]), int(mine[-1]) + 1
+    rs = g.readset(targets=(lo, hi))
+    g.close()
+    import hashlib
+    store = hashlib.sha1(rs.seqs.tobytes() + rs.quals.tobytes()).hexdigest()
+    vals = torch.tensor([float(len(rs.ovl9)), float(len(rs.cigars)), float(hi - lo)], dtype=torch.float64)
+    gathered = [torch.zeros_like(vals) for _ in range(world)]
+    dist.all_gather(gathered, vals)
+    q.put((rank, store, lo, hi, [g_.tolist() for g_ in gathered]))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_generation_covers_the_job_once():
+    import torch.multiprocessing as mp
+    from tools import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 7) % 2000)
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=180) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    (r0, s0, lo0, hi0, g0), (r1, s1, lo1, hi1, g1) = res
+    assert s0 == s1                                   # every rank holds the same read store
+    assert lo0 == 0 and hi0 == lo1 and hi1 == 100     # contiguous shards covering the job exactly once
+    assert g0 == g1                                   # the gathered totals agree on both ranks
+    whole = synth.generate(120, 6000, seed=5, coverage=15.0, min_ovl=1200, targets=(0, 100))
+    assert sum(x[0] for x in g0) == len(whole.ovl9) and sum(x[1] for x in g0) == len(whole.cigars)
