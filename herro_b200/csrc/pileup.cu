@@ -15,13 +15,14 @@
 //     I op of n bases after position p       ->  rows row(p)+1 .. row(p)+n
 // Each range contributes two toggle bits (start, end); a prefix-XOR over the toggle bitmap turns
 // them into "inside a range" masks (M ranges are additionally ANDed with the window's base-row
-// mask).  One CTA per window.  Rows are composed in groups of FOUR consecutive rows: per column
-// a lane reads the group's 4 consume bits, fetches the <= 4 consumed bases (one funnel-shifted
-// word pair of the 2-bit store) and qualities (one unaligned word), expands them with PRMT through
-// a 16-entry selector table, and transposes 4x4 byte blocks so that rows come out row-major.  A
-// group's 32 columns are split over 4 adjacent lanes (8 bytes of every row each).  Class counts
-// for get_supported / the majority vote are five 6-bit fields of one word per row, summed over
-// the 4 lanes by shuffles.
+// mask).  One CTA per window; a thread then owns FOUR consecutive rows: per column it reads the
+// 4 consume bits, fetches the <= 4 consumed bases (one funnel-shifted word pair of the 2-bit
+// store) and qualities (one unaligned word), expands them with PRMT through a 16-entry selector
+// table, and after every 4 columns transposes the 4x4 byte block so that a row's 32 tokens /
+// qualities end up in 8+8 registers that are stored row-major with 16-byte stores.  Class counts
+// for get_supported / the majority vote are five 6-bit fields of one word per row.
+// (Measured alternative, reverted: a group's columns split over 4 lanes — 64 registers, 4 CTAs per
+// SM — was 20 % slower: the shared-memory pipe, not occupancy, limits the compose loop.)
 //
 // The former kernel (features.cu: k_pass2b) walked every target position of every column with
 // scalar byte stores into a shared-memory tile and was instruction bound (1.28 G
@@ -69,7 +70,7 @@ __device__ __forceinline__ uint32_t prefix_xor32(uint32_t x) {  // bit i = parit
     return x;
 }
 
-__global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
+__global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* TM = (uint32_t*)smem_raw;                 // [32][P_CW] toggles -> "inside an M range" -> consume bitmap
     uint32_t* TI = TM + 32 * P_CW;                      // [32][P_CW] toggles -> "inside an insertion"
@@ -262,27 +263,23 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
             if (lane == 31) s_tot[item] = inc;
         }
         __syncthreads();
-        // ---- E: compose rows.  Four consecutive rows (one nibble of every bitmap word) form a group; the group's 32 columns are
-        //      split over 4 adjacent lanes (8 columns each, 16 data registers per lane, which is what lets 4 CTAs share an SM).  For the
-        //      row-wise work (get_supported, majority vote, SupportedPos) lane q of the quartet then owns row q of the group, so thread
-        //      order == row order.
+        // ---- E: compose rows.  A thread owns 4 consecutive rows (one nibble of every bitmap word).
         const uint32_t ngroups = (nrows + 3) >> 2;
-        const int cq = tid & 3;                       // column quarter: columns [8 cq, 8 cq + 8)
-        const int qbase = lane & ~3;                  // first lane of this quartet
-        for (uint32_t g0 = 0; g0 < ngroups; g0 += 64) {
-            const uint32_t g = g0 + ((uint32_t)tid >> 2);
+        for (uint32_t g0 = 0; g0 < ngroups; g0 += 256) {
+            const uint32_t g = g0 + tid;
             const bool act = g < ngroups;
-            uint32_t tw[4][2], qw[4][2], acc[4] = {0, 0, 0, 0};
+            uint32_t tw[4][8], qw[4][8], acc[4] = {0, 0, 0, 0};
             const uint32_t r0 = act ? 4u * g : 0u;
             const uint32_t wi = r0 >> 5, bsh = r0 & 31u, lowmask = (1u << bsh) - 1u;
             const uint32_t row0 = c0 + r0;
             if (act) {
 #pragma unroll
-                for (int c4 = 0; c4 < 2; c4++) {
+                for (int c4 = 0; c4 < 8; c4++) {
                     uint32_t tcol[4], qcol[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
-                        const int c = cq * 8 + c4 * 4 + e;  // column 31 (the pad byte of the 32-byte row) is a padding column: '.' / '!'
+                        const int c = c4 * 4 + e;
+                        if (c == 31) { tcol[e] = TOK_NONE * 0x01010101u; qcol[e] = QUAL_EMPTY * 0x01010101u; continue; }  // pad byte of the 32-byte row
                         const ColA ca = colA[c];
                         const ColB cb = colB[c];
                         const ColC cc = colC[c];
@@ -310,7 +307,7 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
                         tcol[e] = __byte_perm(v, fill, sel);
                         qcol[e] = __byte_perm(qv, QUAL_EMPTY * 0x01010101u, sel);
                     }
-                    // 4x4 byte transpose: tcol[e] byte k = (row k, column 8*cq + 4*c4 + e)  ->  tw[k][c4] byte e
+                    // 4x4 byte transpose: tcol[e] byte k = (row k, column 4*c4+e)  ->  tw[k][c4] byte e
                     {
                         const uint32_t t0 = __byte_perm(tcol[0], tcol[1], 0x5140u), t1 = __byte_perm(tcol[2], tcol[3], 0x5140u);
                         const uint32_t t2 = __byte_perm(tcol[0], tcol[1], 0x7362u), t3 = __byte_perm(tcol[2], tcol[3], 0x7362u);
@@ -328,53 +325,46 @@ __global__ void __launch_bounds__(256, 4) k_pileup(BatchView b) {
                         acc[k] += cls_s[pr & 0xffu] + cls_s[pr >> 16];
                     }
                 }
-                // row-major stores: this lane's 8 bytes of each of the 4 rows (a quartet writes whole 32-byte rows)
+            }
+            // ---- per-row work: second get_supported (thresh 3), majority vote, row-major stores
+            uint32_t supm = 0;  // bit k: row k of this group is supported
+            if (act) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t row = row0 + k;
-                    if (row < L) {
-                        *(uint2*)(b.mat_bases + (rowbase + row) * ROW_BYTES + cq * 8) = make_uint2(tw[k][0], tw[k][1]);
-                        *(uint2*)(b.mat_quals + (rowbase + row) * ROW_BYTES + cq * 8) = make_uint2(qw[k][0], qw[k][1]);
+                    if (row >= L) break;
+                    // second get_supported: >= 2 classes with >= 3 reads (adding 29 to a 6-bit field sets its bit 5 iff count >= 3)
+                    const uint32_t a6 = acc[k];
+                    const bool sup = __popc((a6 + 29u * 0x01041041u) & 0x20820820u) >= 2;
+                    // two most common classes, stable on ties (A<C<G<T<*): keys (count << 3 | 7 - class), top two by a max/min chain
+                    uint32_t ka = ((a6 & 63u) << 3) | 7u, kb = 0u;
+#pragma unroll
+                    for (int q = 1; q < 5; q++) {
+                        const uint32_t kq = (((a6 >> (6 * q)) & 63u) << 3) | (uint32_t)(7 - q);
+                        kb = max(kb, min(ka, kq));
+                        ka = max(ka, kq);
                     }
+                    const uint32_t b0 = 7u - (ka & 7u), b1 = 7u - (kb & 7u), m0 = ka >> 3, m1 = kb >> 3;
+                    const uint32_t tb = tw[k][0] & 0xffu;  // target column, token 0..4
+                    const uint32_t base = (m0 < 2u || (m0 == m1 && (b0 == tb || b1 == tb))) ? tb : b0;
+                    const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
+                    b.row_emit[rowbase + row] = (uint8_t)(emit | (sup ? 0x80u : 0u));
+                    supm |= (sup ? 1u : 0u) << k;
+                    uint4* gb = (uint4*)(b.mat_bases + (rowbase + row) * ROW_BYTES);
+                    uint4* gq = (uint4*)(b.mat_quals + (rowbase + row) * ROW_BYTES);
+                    gb[0] = make_uint4(tw[k][0], tw[k][1], tw[k][2], tw[k][3]); gb[1] = make_uint4(tw[k][4], tw[k][5], tw[k][6], tw[k][7]);
+                    gq[0] = make_uint4(qw[k][0], qw[k][1], qw[k][2], qw[k][3]); gq[1] = make_uint4(qw[k][4], qw[k][5], qw[k][6], qw[k][7]);
                 }
             }
-            // ---- per-row work: lane q of the quartet takes row q.  Class counts summed over the quartet, target token from lane 0.
-            uint32_t a6 = 0, tb = 0;
+            // supported rows are only flagged here: 8 adjacent lanes hold the 8 nibbles of one bitmap word; the ordered list is
+            // built once per chunk below, so this loop has no block-wide barrier
             {
-                const uint32_t tbw = (tw[0][0] & 0xffu) | ((tw[1][0] & 0xffu) << 8) | ((tw[2][0] & 0xffu) << 16) | (tw[3][0] << 24);
-                const uint32_t tb4 = __shfl_sync(HB_FULL, act ? tbw : 0u, qbase);
-                tb = (tb4 >> (8 * cq)) & 0xffu;  // target column (column 0 lives in quarter 0), token 0..4
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint32_t v = act ? acc[k] : 0u;
-                    v += __shfl_xor_sync(HB_FULL, v, 1);
-                    v += __shfl_xor_sync(HB_FULL, v, 2);
-                    if (k == cq) a6 = v;
-                }
-            }
-            bool sup = false;
-            const uint32_t rl = r0 + (uint32_t)cq;  // chunk-local row of this lane
-            if (act && c0 + rl < L) {
-                // second get_supported: >= 2 classes with >= 3 reads (adding 29 to a 6-bit field sets its bit 5 iff count >= 3)
-                sup = __popc((a6 + 29u * 0x01041041u) & 0x20820820u) >= 2;
-                // two most common classes, stable on ties (A<C<G<T<*): keys (count << 3 | 7 - class), top two by a max/min chain
-                uint32_t ka = ((a6 & 63u) << 3) | 7u, kb = 0u;
-#pragma unroll
-                for (int q = 1; q < 5; q++) {
-                    const uint32_t kq = (((a6 >> (6 * q)) & 63u) << 3) | (uint32_t)(7 - q);
-                    kb = max(kb, min(ka, kq));
-                    ka = max(ka, kq);
-                }
-                const uint32_t b0 = 7u - (ka & 7u), b1 = 7u - (kb & 7u), m0 = ka >> 3, m1 = kb >> 3;
-                const uint32_t base = (m0 < 2u || (m0 == m1 && (b0 == tb || b1 == tb))) ? tb : b0;
-                const uint32_t emit = nsel >= 2 ? base : 4u;  // n_alns < 2: window dropped (src/consensus.rs:104-111)
-                b.row_emit[rowbase + c0 + rl] = (uint8_t)(emit | (sup ? 0x80u : 0u));
-            }
-            // supported rows are only flagged here (a warp's 32 lanes are 32 consecutive rows = one word of the bitmap);
-            // the ordered list is built once per chunk below, so this loop has no block-wide barrier
-            {
-                const uint32_t bal = __ballot_sync(HB_FULL, sup);
-                if (lane == 0 && (g0 >> 3) + (uint32_t)warp < cw) supbits[(g0 >> 3) + warp] = bal;
+                uint32_t v = supm << (4 * (lane & 7));
+                v |= __shfl_xor_sync(HB_FULL, v, 1);
+                v |= __shfl_xor_sync(HB_FULL, v, 2);
+                v |= __shfl_xor_sync(HB_FULL, v, 4);
+                const uint32_t wj = (g0 >> 3) + (uint32_t)warp * 4u + ((uint32_t)lane >> 3);
+                if ((lane & 7) == 0 && wj < cw) supbits[wj] = v;
             }
         }
         __syncthreads();
