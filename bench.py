@@ -212,7 +212,9 @@ def gpu_numa_cpus(local_rank):
 
 
 def workload_name(args):
-    return (f"cfg3: synthetic {args.reads} reads x {args.read_len} bp, {args.profile} profile, 40x, W={args.window}, "
+    # BASELINE.json configs: cfg2 10k x 15 kb R10 -b 64; cfg3 50k x 20 kb R10 -b 128 (the default); cfg4 100 kb reads; cfg5 R9 profile 15 kb
+    name = "cfg5" if args.profile == "r9" else ("cfg4" if args.read_len >= 50000 else ("cfg2" if args.read_len <= 15000 else "cfg3"))
+    return (f"{name}: synthetic {args.reads} reads x {args.read_len} bp, {args.profile} profile, 40x, W={args.window}, "
             f"-b {args.batch_size}")
 
 

@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t prefix_xor32(uint32_t x) {  // bit i = parit
     return x;
 }
 
+template <bool SUPSYNC>  // SUPSYNC: the supported-row list is appended inside the compose loop (3 barriers per 1024 rows); A-B timing aid
 __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* TM = (uint32_t*)smem_raw;                 // [32][P_CW] toggles -> "inside an M range" -> consume bitmap
@@ -356,9 +357,34 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
                     gq[0] = make_uint4(qw[k][0], qw[k][1], qw[k][2], qw[k][3]); gq[1] = make_uint4(qw[k][4], qw[k][5], qw[k][6], qw[k][7]);
                 }
             }
+            if constexpr (SUPSYNC) {
+                const uint32_t nf = __popc(supm);
+                const uint32_t inc = warp_incl_scan(nf, lane);
+                if (lane == 31) s_warp[warp] = inc;
+                __syncthreads();
+                uint32_t off = s_nsup + inc - nf;
+                for (int k = 0; k < warp; k++) off += s_warp[k];
+                if (nf) {
+                    const uint32_t insw = ins[wi];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (!((supm >> k) & 1u)) continue;
+                        const uint32_t rl = r0 + k;
+                        const uint32_t basew = ~insw;
+                        const uint32_t upto = (rl & 31u) == 31u ? basew : (basew & ((2u << (rl & 31u)) - 1u));
+                        const uint32_t p = s_pcarry + (uint32_t)bpref[wi] + __popc(upto) - 1u;
+                        const uint32_t kk = (c0 + rl) - rm[p];
+                        b.sup_row[rowbase + off] = c0 + rl;
+                        b.sup_pk[rowbase + off] = (p << 8) | (kk & 0xffu);
+                        off++;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_nsup += t; }
+                __syncthreads();
+            } else {
             // supported rows are only flagged here: 8 adjacent lanes hold the 8 nibbles of one bitmap word; the ordered list is
             // built once per chunk below, so this loop has no block-wide barrier
-            {
                 uint32_t v = supm << (4 * (lane & 7));
                 v |= __shfl_xor_sync(HB_FULL, v, 1);
                 v |= __shfl_xor_sync(HB_FULL, v, 2);
@@ -369,7 +395,7 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
         }
         __syncthreads();
         // ---- ordered list of supported rows of the chunk: (row, pos << 8 | ins), appended in row order
-        if (warp == 0) {
+        if (!SUPSYNC && warp == 0) {
             uint32_t cnt[P_WPL], sum = 0;
 #pragma unroll
             for (int i = 0; i < P_WPL; i++) {
@@ -415,10 +441,17 @@ size_t pileup_smem() {
            (16 + 256) * 4 + 64;
 }
 
+static bool g_supsync = false;
 cudaError_t pileup_configure() {
-    return cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
+    g_supsync = getenv("HERRO_B200_PILEUP_SUPSYNC") != nullptr;  // read once, at context creation
+    cudaError_t e = cudaFuncSetAttribute(k_pileup<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pileup<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
 }
 
-void launch_pileup_v2(const BatchView& b, cudaStream_t st) { k_pileup<<<b.n_win, 256, pileup_smem(), st>>>(b); }
+void launch_pileup_v2(const BatchView& b, cudaStream_t st) {
+    if (g_supsync) k_pileup<true><<<b.n_win, 256, pileup_smem(), st>>>(b);
+    else k_pileup<false><<<b.n_win, 256, pileup_smem(), st>>>(b);
+}
 
 }  // namespace hb
