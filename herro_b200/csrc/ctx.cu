@@ -1226,6 +1226,7 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     ctx->wt.no_fuse_ln = getenv("HERRO_B200_NO_FUSE_LN") != nullptr;
     ctx->wt.no_fuse_ffn = getenv("HERRO_B200_NO_FUSE_FFN") != nullptr;
     ctx->wt.no_fuse_attn = getenv("HERRO_B200_NO_FUSE_ATTN") != nullptr;
+    ctx->wt.no_fuse_oproj = getenv("HERRO_B200_NO_FUSE_OPROJ") != nullptr;
     if (!getenv("HERRO_B200_NO_NUMA_BIND")) probe_numa(ctx);
     for (int li = 0; li < ctx->n_lanes; li++) {
         auto& L = ctx->lanes[li];

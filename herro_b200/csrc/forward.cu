@@ -325,6 +325,8 @@ struct FwdWs {
     size_t bytes;
 };
 static bool ffn_is_fused(const FwdWeights& wt) { return wt.C == 128 && wt.F == 512 && !wt.no_fuse_ln && !wt.no_fuse_ffn; }
+// the attention out-projection (+ residual + ln2) runs inside the fused FFN kernel
+static bool oproj_in_ffn(const FwdWeights& wt) { return ffn_is_fused(wt) && !wt.no_fuse_oproj; }
 static FwdWs carve(const FwdWeights& wt, size_t npos, uint8_t* base) {
     const size_t np = (npos + 127) / 128 * 128;  // positions padded to a GEMM tile
     const size_t T = np * TOK_PER_POS;
@@ -403,8 +405,9 @@ void forward_class_flops_per_pos(const FwdWeights& wt, uint64_t (&out)[16]) {
     const uint64_t qkv = S * 2 * C * 3 * C, attn = (uint64_t)wt.H * 2 * 2 * S * S * dh, oproj = S * 2 * C * C, ffn = S * 2 * 2 * C * F;
     if (attn_is_fused(wt)) out[K_QKV_ATTN] = L * (qkv + attn);
     else { out[K_GEMM] += L * qkv; out[K_ATTENTION] = L * attn; }
-    out[K_GEMM] += L * oproj + 2 * S * C * D;
-    if (ffn_is_fused(wt)) out[K_FFN] = L * ffn; else out[K_GEMM] += L * ffn;
+    out[K_GEMM] += 2 * S * C * D;
+    if (oproj_in_ffn(wt)) out[K_FFN] += L * oproj; else out[K_GEMM] += L * oproj;
+    if (ffn_is_fused(wt)) out[K_FFN] += L * ffn; else out[K_GEMM] += L * ffn;
     out[K_HEADS] = 2 * D * 6;
 }
 
@@ -464,7 +467,9 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
         }
         // out-proj + residual (+ LN2 -> split H).  In-place on H is safe: a row's outputs are written by the
         // thread that owns the row only after every MMA that reads the tile has completed (tfull barrier).
-        if (fuse_ln) {
+        if (oproj_in_ffn(wt)) {
+            // nothing here: k_ffn_ws<true> applies Wo, the residual and ln2 to the attention output itself
+        } else if (fuse_ln) {
             gemm_ln(wt, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ly.ln2_g, ly.ln2_b, ws.Hhi, ws.Hlo, T, C, st, kt); nl++;
         } else {
             gemm(wt, GEMM_OUT_F32_RES, ws.Hhi, ws.Hlo, C, ly.s_o, ly.bo, ws.X, ws.X, C, nullptr, nullptr, 0, T, C, C, st, kt); nl++;
@@ -478,6 +483,10 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
             FfnArgs fa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_1.hi, (const __nv_bfloat16*)ly.s_1.lo,
                        (const __nv_bfloat16*)ly.s_2.hi, (const __nv_bfloat16*)ly.s_2.lo, ly.b1, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo,
                        (uint32_t)F, (uint32_t)(T / 128)};
+            if (oproj_in_ffn(wt)) {
+                fa.Wohi = (const __nv_bfloat16*)ly.s_o.hi; fa.Wolo = (const __nv_bfloat16*)ly.s_o.lo;
+                fa.bo = ly.bo; fa.ln2_g = ly.ln2_g; fa.ln2_b = ly.ln2_b;
+            }
             kt.begin(K_FFN); ffn_tc(fa, wt.num_sms, st); kt.end(); nl++;
             continue;
         }

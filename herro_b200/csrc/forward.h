@@ -35,7 +35,7 @@ struct FwdWeights {
     int stem_kblocks = 0;   // 0: tensor-core stem unavailable (C != 128 or too many taps)
     int num_sms;
     // debugging aids / A-B parity tests, read from the environment ONCE in hb_create (HERRO_B200_NO_FUSE_{LN,FFN,ATTN})
-    int no_fuse_ln = 0, no_fuse_ffn = 0, no_fuse_attn = 0;
+    int no_fuse_ln = 0, no_fuse_ffn = 0, no_fuse_attn = 0, no_fuse_oproj = 0;
 };
 
 // gemm_tc.cu
@@ -65,6 +65,10 @@ struct FfnArgs {  // k_ffn_ws: fused FFN for C == 128, F == 512
     const float *ln_g, *ln_b;              // LayerNorm that follows
     __nv_bfloat16 *out_hi, *out_lo;        // LayerNorm(X_new), split bf16, [T][128]
     uint32_t F, m_tiles;
+    // fused attention out-projection (k_ffn_ws<true>): Hhi/Hlo then hold the attention output O, and the kernel first computes
+    // X += O · Wo^T + bo, H = LayerNorm(X; ln2) on chip.  Wohi == nullptr: unfused (H is read as given).
+    const __nv_bfloat16 *Wohi = nullptr, *Wolo = nullptr;  // [128][128]
+    const float *bo = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
 };
 cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st);
 struct QkvAttnArgs {  // k_qkv_attn_ws: QKV projection + read-axis attention for C == 128, 4 heads

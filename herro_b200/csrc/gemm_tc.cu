@@ -130,6 +130,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 fp32 columns of this thread's TMEM lane (its row) written back: parks a row of the residual stream on chip
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // ---- row-owner <-> coalesced transposes through a per-warp shared-memory buffer ---------------------------------------
 // In the epilogues a thread owns one row (its TMEM lane).  Touching global memory directly from that layout issues
@@ -436,19 +449,29 @@ __device__ __forceinline__ void ffn_step(int i, int& is2, int& c) {
 }
 constexpr int FFN_STAGES = 2;  // 2 x 64 KB operand tiles + 2 x 32 KB ring = 192 KB
 
+// FUSE_O: the attention out-projection, its residual add and LayerNorm (ln2) run in front of the FFN inside this kernel:
+//   P0   : accO = O · Wo^T                       (O = attention output tile, loaded where H used to be)
+//   E0   : X' = accO + bo + X  ->  parked in 128 spare TMEM columns (fp32, one row per lane);  H = LN2(X') -> split bf16 ->
+//          written over the O tile in shared memory (it is the A operand of FFN1)
+//   ...  : FFN as above, and the final epilogue takes its residual X' from TMEM instead of HBM.
+// This removes the HBM-bound out-projection kernel (it re-read and re-wrote the fp32 residual stream: 256 KB per 128-token
+// tile and layer).  Cost: accO is single-buffered (its second buffer holds X'), so the next tile's P0 waits for this tile's
+// final epilogue to drain the accumulator.
+template <bool FUSE_O>
 __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid_constant__ CUtensorMap tmHhi,
                                                         const __grid_constant__ CUtensorMap tmHlo, const __grid_constant__ CUtensorMap tmW1hi,
                                                         const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmW2hi,
-                                                        const __grid_constant__ CUtensorMap tmW2lo) {
+                                                        const __grid_constant__ CUtensorMap tmW2lo, const __grid_constant__ CUtensorMap tmWohi,
+                                                        const __grid_constant__ CUtensorMap tmWolo) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
     uint8_t* sA2 = sA1 + FFN_A_BYTES;               // relu(hidden chunk) tile, same layout
     uint8_t* ring = sA2 + FFN_A_BYTES;              // FFN_STAGES x FFN_RING_BYTES
     __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full, a2_empty,
-        o_full[2], o_empty[2];
+        o_full[2], o_empty[2], y_full, h_full;
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN];
+    __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN], s_bo[BN], s_ln2g[BN], s_ln2b[BN];
     __shared__ float s_red[2][2][BM];  // [tile parity][column half][row]: LayerNorm partial sums
     __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
 
@@ -461,6 +484,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&a1_full, 1); mbar_init(&a1_empty, 1);
         mbar_init(&a2_full, G_EPI); mbar_init(&a2_empty, 1);
+        mbar_init(&y_full, 1); mbar_init(&h_full, G_EPI);
         for (int a = 0; a < 2; a++) {
             mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], G_EPI);
             mbar_init(&o_full[a], 1); mbar_init(&o_empty[a], G_EPI);
@@ -469,11 +493,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
     }
     for (int i = tid; i < 512; i += G_THREADS) s_b1[i] = g.b1[i];
     if (tid < BN) { s_b2[tid] = g.b2[tid]; s_lng[tid] = g.ln_g[tid]; s_lnb[tid] = g.ln_b[tid]; }
+    if (FUSE_O && tid < BN) { s_bo[tid] = g.bo[tid]; s_ln2g[tid] = g.ln2_g[tid]; s_ln2b[tid] = g.ln2_b[tid]; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    // TMEM columns: accF[0] 0..127, accF[1] 128..255, accO[0] 256..383, accO[1] 384..511
+    // TMEM columns: accF[0] 0..127, accF[1] 128..255, accO[0] 256..383, accO[1] 384..511 (FUSE_O: accO 256..383, X' 384..511)
 
     if (warp == G_PROD_WARP) {
         // =============================== producer: one lane issues the TMA copies ===============================
@@ -487,6 +512,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 for (int kb = 0; kb < 2; kb++) {
                     tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128), &tmHhi, &a1_full, kb * BK, m0);
                     tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128) + BM * 128, &tmHlo, &a1_full, kb * BK, m0);
+                }
+                if (FUSE_O) {  // Wo: 2 k-block tiles, ahead of the FFN weights
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
+                        mbar_arrive_expect_tx(&full_bar[s], FFN_RING_BYTES);
+                        tma_load_2d(sb, &tmWohi, &full_bar[s], kb * BK, 0);
+                        tma_load_2d(sb + BN * 128, &tmWolo, &full_bar[s], kb * BK, 0);
+                    }
                 }
                 // ---- the 16 weight k-block tiles of this tile, in MMA issue order
                 for (int st = 0; st < 8; st++) {
@@ -511,8 +546,33 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             uint32_t it_stage = 0, n_done = 0, nf[2] = {0, 0}, na2 = 0;
             const uint32_t a1b = smem_u32(sA1), a2b = smem_u32(sA2);
             for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
-                const uint32_t oacc = n_done & 1;
+                const uint32_t oacc = FUSE_O ? 0u : (n_done & 1);
                 mbar_wait(&a1_full, n_done & 1);
+                if (FUSE_O) {
+                    // ---- P0: accO = O · Wo^T (the previous tile's final epilogue must have drained accO)
+                    mbar_wait(&o_empty[0], (n_done & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + 2 * BN;
+                    for (int kb = 0; kb < 2; kb++, it_stage++) {
+                        const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
+                        const uint64_t dAh = make_desc(a1b + kb * (2 * BM * 128)), dAl = make_desc(a1b + kb * (2 * BM * 128) + BM * 128);
+                        const uint64_t dBh = make_desc(sb), dBl = make_desc(sb + BN * 128);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            mma_bf16(tmem_d, dAh + adv, dBh + adv, (kb | k) ? 1u : 0u);
+                            mma_bf16(tmem_d, dAl + adv, dBh + adv, 1u);
+                            mma_bf16(tmem_d, dAh + adv, dBl + adv, 1u);
+                        }
+                        umma_commit(&empty_bar[s]);
+                    }
+                    umma_commit(&y_full);
+                    mbar_wait(&h_full, n_done & 1);  // E0 has replaced the O tile by H = LN2(X') in shared memory
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 for (int st = 0; st < 8; st++) {
                     int is2, c;
                     ffn_step(st, is2, c);
@@ -524,7 +584,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                         abase = a1b;
                     } else {
                         mbar_wait(&a2_full, na2 & 1);             // E1(c) has written the hidden chunk
-                        if (c == 0) mbar_wait(&o_empty[oacc], ((n_done >> 1) & 1) ^ 1);
+                        if (!FUSE_O && c == 0) mbar_wait(&o_empty[oacc], ((n_done >> 1) & 1) ^ 1);
                         tmem_d = tmem_base + 2 * BN + oacc * BN;
                         abase = a2b;
                     }
@@ -566,9 +626,69 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
             const uint32_t r = wq * 32 + lane;
             const size_t row = (size_t)tile * BM + r;
-            {   // the residual rows this thread adds in the final epilogue (~10 us from now): start them towards L2
+            if (!FUSE_O) {   // the residual rows this thread adds in the final epilogue (~10 us from now): start them towards L2
                 const float* pr = g.X + row * BN + ch;
                 prefetch_l2(pr); prefetch_l2(pr + 32);
+            }
+            if (FUSE_O) {
+                // ---- E0: X' = accO + bo + X (parked in TMEM), H = LN2(X') -> split bf16 -> over the O tile (A operand of FFN1)
+                float4 pre[4];
+                float* stg = s_stage[warp];
+                const float* xblk = g.X + ((size_t)tile * BM + wq * 32) * BN + ch;
+                warp_ldg_f32x16(lane, xblk, BN, pre);  // requested before the wait for the MMAs
+                mbar_wait(&y_full, n_done & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + 2 * BN + ch + ((uint32_t)(wq * 32) << 16);
+                const uint32_t txs = tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16);
+                float x[64];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tacc + (uint32_t)c0, v);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        float rv[16];
+                        warp_xpose_f32x16(stg, lane, pre, rv);
+                        if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, BN, pre);
+#pragma unroll
+                        for (int jj = 0; jj < 16; jj++) {
+                            x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_bo[ch + c0 + h * 16 + jj] + rv[jj];
+                            v[h * 16 + jj] = __float_as_uint(x[c0 + h * 16 + jj]);
+                        }
+                    }
+                    tmem_st32(txs + (uint32_t)c0, v);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 64; jj++) sum += x[jj];
+                s_red[0][eh][r] = sum;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float mean = (s_red[0][0][r] + s_red[0][1][r]) * (1.f / BN);
+                float var = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 64; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                s_red[0][eh][r] = var;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float rstd = rsqrtf((s_red[0][0][r] + s_red[0][1][r]) * (1.f / BN) + 1e-5f);
+                uint8_t* a1row = sA1 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; q8++) {  // 8 x 8 channels = 8 x 16-byte chunks of hi and of lo
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const int jj = q8 * 8 + e;
+                        const float a = (x[jj] - mean) * rstd * s_ln2g[ch + jj] + s_ln2b[ch + jj];
+                        const float bq = (x[jj + 1] - mean) * rstd * s_ln2g[ch + jj + 1] + s_ln2b[ch + jj + 1];
+                        split2(a, bq, hi[e >> 1], lo[e >> 1]);
+                    }
+                    const uint32_t off = (uint32_t)((q8 ^ (r & 7)) << 4);
+                    *(uint4*)(a1row + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *(uint4*)(a1row + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of H -> tensor core
+                mbar_arrive(&h_full);
             }
             for (int c = 0; c < 4; c++) {
                 // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major; this thread's 64 columns = k-block eh)
@@ -604,10 +724,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 mbar_arrive(&a2_full);
             }
             // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16 (partial sums exchanged between the halves)
-            const uint32_t oacc = n_done & 1;
+            const uint32_t oacc = FUSE_O ? 0u : (n_done & 1);
             float4 pre[4];  // first residual block: requested before the wait for the last MMAs (it does not depend on them)
-            warp_ldg_f32x16(lane, g.X + ((size_t)tile * BM + wq * 32) * BN + ch, BN, pre);
-            mbar_wait(&o_full[oacc], (n_done >> 1) & 1);
+            if (!FUSE_O) warp_ldg_f32x16(lane, g.X + ((size_t)tile * BM + wq * 32) * BN + ch, BN, pre);
+            mbar_wait(&o_full[oacc], FUSE_O ? (n_done & 1) : ((n_done >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ch + ((uint32_t)(wq * 32) << 16);
             float x[64];
@@ -617,15 +737,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (FUSE_O) {  // the residual X' of this row was parked in TMEM by E0
+                    uint32_t xr[32];
+                    tmem_ld32(tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, xr);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    float rv[16];
-                    warp_xpose_f32x16(stg, lane, pre, rv);
-                    if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, BN, pre);
+                    for (int jj = 0; jj < 32; jj++) x[c0 + jj] = __uint_as_float(v[jj]) + s_b2[ch + c0 + jj] + __uint_as_float(xr[jj]);
+                    warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                    warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
+                } else {
 #pragma unroll
-                    for (int jj = 0; jj < 16; jj++)
-                        x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_b2[ch + c0 + h * 16 + jj] + rv[jj];
-                    warp_store_f32x16(stg, lane, xblk + c0 + h * 16, BN, x + c0 + h * 16);
+                    for (int h = 0; h < 2; h++) {
+                        float rv[16];
+                        warp_xpose_f32x16(stg, lane, pre, rv);
+                        if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, BN, pre);
+#pragma unroll
+                        for (int jj = 0; jj < 16; jj++)
+                            x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_b2[ch + c0 + h * 16 + jj] + rv[jj];
+                        warp_store_f32x16(stg, lane, xblk + c0 + h * 16, BN, x + c0 + h * 16);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -633,16 +762,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             float sum = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) sum += x[jj];
-            s_red[oacc][eh][r] = sum;
+            const uint32_t rs_ = FUSE_O ? 1u : oacc;
+            s_red[rs_][eh][r] = sum;
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            const float mean = (s_red[oacc][0][r] + s_red[oacc][1][r]) * (1.f / BN);
+            const float mean = (s_red[rs_][0][r] + s_red[rs_][1][r]) * (1.f / BN);
             float var = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            s_red[oacc][eh][r] = var;
+            s_red[rs_][eh][r] = var;
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            const float rstd = rsqrtf((s_red[oacc][0][r] + s_red[oacc][1][r]) * (1.f / BN) + 1e-5f);
+            const float rstd = rsqrtf((s_red[rs_][0][r] + s_red[rs_][1][r]) * (1.f / BN) + 1e-5f);
             __nv_bfloat16* hblk = g.out_hi + ((size_t)tile * BM + wq * 32) * BN + ch;
             __nv_bfloat16* lblk = g.out_lo + ((size_t)tile * BM + wq * 32) * BN + ch;
 #pragma unroll
@@ -1321,17 +1451,25 @@ cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
     const size_t smem = (size_t)2 * FFN_A_BYTES + (size_t)FFN_STAGES * FFN_RING_BYTES + 1024;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_ffn_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_ffn_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (a.m_tiles == 0) return cudaSuccess;
-    CUtensorMap tHh, tHl, t1h, t1l, t2h, t2l;
+    CUtensorMap tHh, tHl, t1h, t1l, t2h, t2l, toh, tol;
     const uint64_t T = (uint64_t)a.m_tiles * BM;
     if (!make_tmap(&tHh, a.Hhi, T, BN, BN) || !make_tmap(&tHl, a.Hlo, T, BN, BN) || !make_tmap(&t1h, a.W1hi, a.F, BN, BN) ||
         !make_tmap(&t1l, a.W1lo, a.F, BN, BN) || !make_tmap(&t2h, a.W2hi, BN, a.F, a.F) || !make_tmap(&t2l, a.W2lo, BN, a.F, a.F))
         return cudaErrorInvalidValue;
-    k_ffn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l);
+    const unsigned grid = (unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms);
+    if (a.Wohi) {
+        if (!make_tmap(&toh, a.Wohi, BN, BN, BN) || !make_tmap(&tol, a.Wolo, BN, BN, BN)) return cudaErrorInvalidValue;
+        k_ffn_ws<true><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, toh, tol);
+    } else {
+        k_ffn_ws<false><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, t1h, t1l);
+    }
     return cudaGetLastError();
 }
 

@@ -134,10 +134,11 @@ def test_fused_qkv_attention_equals_unfused(monkeypatch):
     assert worst <= 1e-4, worst
 
 
-@pytest.mark.parametrize("env", ["HERRO_B200_NO_FUSE_FFN", "HERRO_B200_NO_FUSE_LN"])
+@pytest.mark.parametrize("env", ["HERRO_B200_NO_FUSE_OPROJ", "HERRO_B200_NO_FUSE_FFN", "HERRO_B200_NO_FUSE_LN"])
 def test_fused_ffn_and_layernorm_equal_unfused(monkeypatch, env):
-    """k_ffn_ws (hidden activations on chip, LayerNorm in the epilogue) / the LayerNorm-fused epilogues against the
-    chain of separate contraction and LayerNorm kernels: same emitted bases, logits equal to fp32 rounding noise."""
+    """k_ffn_ws (attention out-projection + residual + LayerNorm in front, hidden activations on chip, LayerNorm in the
+    epilogue) / the LayerNorm-fused epilogues against the chain of separate contraction and LayerNorm kernels: same emitted
+    bases, logits equal to fp32 rounding noise."""
     rs = helpers.small_readset(n_reads=30, mean_len=7000, seed=14)
     model = helpers.model_path(seed=3)
     a = helpers.run_product(rs, model, 4096, 64, keep_debug=True)
