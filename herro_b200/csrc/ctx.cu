@@ -227,7 +227,7 @@ struct hb_ctx {
 
     // staging: every submitting (feature) thread fills its own batch without taking the context lock;
     // full batches are handed to the launch worker's queue
-    struct ThreadSlot { std::thread::id owner; HostBatch batch; };
+    struct ThreadSlot { std::thread::id owner; HostBatch batch; uint32_t handed = 0; /* batches handed over since the last flush */ };
     std::vector<std::unique_ptr<ThreadSlot>> slots;
     PinBuf pin_in;  // staging of hb_upload_reads
     // Launch lanes (stream + device scratch + pinned result buffers each), one worker thread per lane:
@@ -956,7 +956,7 @@ hb_ctx::ThreadSlot* my_slot(hb_ctx* ctx) {
     const auto me = std::this_thread::get_id();
     for (auto& sl : ctx->slots)
         if (sl->owner == me) { tl_ctx = ctx; tl_slot = sl.get(); tl_gen = ctx->generation; return tl_slot; }
-    ctx->slots.emplace_back(new hb_ctx::ThreadSlot{me, HostBatch(ctx->device)});
+    ctx->slots.emplace_back(new hb_ctx::ThreadSlot{me, HostBatch(ctx->device), 0});
     ctx->n_slots.store((uint32_t)ctx->slots.size());
     tl_ctx = ctx; tl_slot = ctx->slots.back().get(); tl_gen = ctx->generation;
     return tl_slot;
@@ -1176,10 +1176,15 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
     // `launch_targets` is shared by the submitting threads: each stages launch_targets / n_threads targets per launch,
     // so the targets in flight (and the latency to the first launch) do not grow with the thread count
     const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
-    const uint32_t thr = std::min(lt, std::max(32u, lt / ns));
+    uint32_t thr = std::min(lt, std::max(32u, lt / ns));
+    // slow start: with several submitting threads, the first batches of each are small (64, 128, 256, ... targets) so that the GPU
+    // has work a few milliseconds after the first submit instead of after a whole launch has been staged (a single submitting
+    // thread keeps exact launch sizes: tests and the isolated launch bench.py times rely on them)
+    if (ns >= 2 && slot->handed < 4) thr = std::min(thr, 64u << slot->handed);
     if (slot->batch.tgt.size() >= thr) {
         std::unique_lock<std::mutex> lk(ctx->mu);
         enqueue_batch(ctx, lk, slot->batch);
+        slot->handed++;
     }
     return HB_OK;
 }
