@@ -70,7 +70,6 @@ __device__ __forceinline__ uint32_t prefix_xor32(uint32_t x) {  // bit i = parit
     return x;
 }
 
-template <bool SUPSYNC>  // SUPSYNC: the supported-row list is appended inside the compose loop (3 barriers per 1024 rows); A-B timing aid
 __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* TM = (uint32_t*)smem_raw;                 // [32][P_CW] toggles -> "inside an M range" -> consume bitmap
@@ -78,13 +77,12 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
     uint32_t* ins = TI + 32 * P_CW;                     // [P_CW] toggles -> rows that are insertion slots (not base rows)
     uint16_t* pref = (uint16_t*)(ins + P_CW);           // [32][P_CW] consumed bases of the column before each word (chunk-local)
     uint16_t* bpref = pref + 32 * P_CW;                 // [P_CW] base rows before each word (chunk-local)
-    uint32_t* supbits = (uint32_t*)(bpref + P_CW);      // [P_CW] rows of the chunk that are supported (second get_supported)
-    ColA* colA = (ColA*)(supbits + P_CW);               // [32]
+    ColA* colA = (ColA*)(bpref + P_CW);                 // [32]
     ColB* colB = (ColB*)(colA + 32);
     ColC* colC = (ColC*)(colB + 32);
     uint32_t* sel_s = (uint32_t*)(colC + 32);           // [16]
     uint32_t* cls_s = sel_s + 16;                       // [256]
-    __shared__ uint32_t s_ow[32], s_x0[32], s_carry[32], s_tot[33], s_warp[8];
+    __shared__ uint32_t s_x0[32], s_carry[32], s_tot[33], s_warp[8];
     __shared__ uint32_t s_opb[32], s_opoff[33];  // op arrays of the columns: first slot, and the exclusive prefix of their op counts
     __shared__ const uint8_t* s_qp0[32];
     __shared__ uint32_t s_nsup, s_pcarry;
@@ -141,7 +139,7 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
         a.w32 = (const uint32_t*)words;
         a.qp = qp0;
         colA[c] = a; colB[c] = bb; colC[c] = cc;
-        s_ow[c] = owi; s_x0[c] = x0; s_qp0[c] = qp0; s_carry[c] = 0;
+        s_x0[c] = x0; s_qp0[c] = qp0; s_carry[c] = 0;
         s_opb[c] = opb_c;
         const uint32_t inc = warp_incl_scan(nops_c, lane);
         s_opoff[c] = inc - nops_c;
@@ -357,7 +355,10 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
                     gq[0] = make_uint4(qw[k][0], qw[k][1], qw[k][2], qw[k][3]); gq[1] = make_uint4(qw[k][4], qw[k][5], qw[k][6], qw[k][7]);
                 }
             }
-            if constexpr (SUPSYNC) {
+            // ---- ordered list of supported rows: (row, pos << 8 | ins) appended in row order.  The three barriers per 1024 rows also
+            //      keep the CTA's warps on the same stretch of every column's query data: a barrier-free variant (supported rows
+            //      flagged in a bitmap, list built once per chunk) measured 20 % SLOWER (0.80 vs 0.67 ms per 2 079 windows).
+            {
                 const uint32_t nf = __popc(supm);
                 const uint32_t inc = warp_incl_scan(nf, lane);
                 if (lane == 31) s_warp[warp] = inc;
@@ -369,64 +370,21 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         if (!((supm >> k) & 1u)) continue;
-                        const uint32_t rl = r0 + k;
+                        const uint32_t rl = r0 + k;  // chunk-local row; base rows at or before it give the target position
                         const uint32_t basew = ~insw;
                         const uint32_t upto = (rl & 31u) == 31u ? basew : (basew & ((2u << (rl & 31u)) - 1u));
                         const uint32_t p = s_pcarry + (uint32_t)bpref[wi] + __popc(upto) - 1u;
                         const uint32_t kk = (c0 + rl) - rm[p];
                         b.sup_row[rowbase + off] = c0 + rl;
-                        b.sup_pk[rowbase + off] = (p << 8) | (kk & 0xffu);
+                        b.sup_pk[rowbase + off] = (p << 8) | (kk & 0xffu);  // SupportedPos.ins is a u8 (H13)
                         off++;
                     }
                 }
                 __syncthreads();
                 if (tid == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_nsup += t; }
                 __syncthreads();
-            } else {
-            // supported rows are only flagged here: 8 adjacent lanes hold the 8 nibbles of one bitmap word; the ordered list is
-            // built once per chunk below, so this loop has no block-wide barrier
-                uint32_t v = supm << (4 * (lane & 7));
-                v |= __shfl_xor_sync(HB_FULL, v, 1);
-                v |= __shfl_xor_sync(HB_FULL, v, 2);
-                v |= __shfl_xor_sync(HB_FULL, v, 4);
-                const uint32_t wj = (g0 >> 3) + (uint32_t)warp * 4u + ((uint32_t)lane >> 3);
-                if ((lane & 7) == 0 && wj < cw) supbits[wj] = v;
             }
         }
-        __syncthreads();
-        // ---- ordered list of supported rows of the chunk: (row, pos << 8 | ins), appended in row order
-        if (!SUPSYNC && warp == 0) {
-            uint32_t cnt[P_WPL], sum = 0;
-#pragma unroll
-            for (int i = 0; i < P_WPL; i++) {
-                const uint32_t j = lane * P_WPL + i;
-                cnt[i] = sum;
-                sum += j < cw ? __popc(supbits[j]) : 0u;
-            }
-            const uint32_t inc = warp_incl_scan(sum, lane);
-#pragma unroll
-            for (int i = 0; i < P_WPL; i++) {
-                const uint32_t j = lane * P_WPL + i;
-                if (j >= cw) continue;
-                uint32_t bits = supbits[j];
-                uint32_t off = s_nsup + inc - sum + cnt[i];
-                const uint32_t basew = ~ins[j];
-                while (bits) {
-                    const uint32_t bi = (uint32_t)__ffs((int)bits) - 1u;
-                    bits &= bits - 1u;
-                    const uint32_t rl = j * 32u + bi;  // chunk-local row; base rows at or before it give the target position
-                    const uint32_t upto = bi == 31u ? basew : (basew & ((2u << bi) - 1u));
-                    const uint32_t p = s_pcarry + (uint32_t)bpref[j] + __popc(upto) - 1u;
-                    const uint32_t kk = (c0 + rl) - rm[p];
-                    b.sup_row[rowbase + off] = c0 + rl;
-                    b.sup_pk[rowbase + off] = (p << 8) | (kk & 0xffu);  // SupportedPos.ins is a u8 (H13)
-                    off++;
-                }
-            }
-            __syncwarp();
-            if (lane == 31) s_nsup += inc;
-        }
-        __syncthreads();
         // ---- carry the per-column consumed-base counts and the base-row count into the next chunk
         if (tid < 32) s_carry[tid] += s_tot[tid];
         if (tid == 32) s_pcarry += s_tot[32];
@@ -436,22 +394,15 @@ __global__ void __launch_bounds__(256, 2) k_pileup(BatchView b) {
 }
 
 size_t pileup_smem() {
-    return (size_t)2 * 32 * P_CW * 4 + (size_t)P_CW * 4 + (size_t)32 * P_CW * 2 + (size_t)P_CW * 2 + (size_t)P_CW * 4 +
+    return (size_t)2 * 32 * P_CW * 4 + (size_t)P_CW * 4 + (size_t)32 * P_CW * 2 + (size_t)P_CW * 2 +
            32 * (sizeof(ColA) + sizeof(ColB) + sizeof(ColC)) +
            (16 + 256) * 4 + 64;
 }
 
-static bool g_supsync = false;
 cudaError_t pileup_configure() {
-    g_supsync = getenv("HERRO_B200_PILEUP_SUPSYNC") != nullptr;  // read once, at context creation
-    cudaError_t e = cudaFuncSetAttribute(k_pileup<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_pileup<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
+    return cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem());
 }
 
-void launch_pileup_v2(const BatchView& b, cudaStream_t st) {
-    if (g_supsync) k_pileup<true><<<b.n_win, 256, pileup_smem(), st>>>(b);
-    else k_pileup<false><<<b.n_win, 256, pileup_smem(), st>>>(b);
-}
+void launch_pileup_v2(const BatchView& b, cudaStream_t st) { k_pileup<<<b.n_win, 256, pileup_smem(), st>>>(b); }
 
 }  // namespace hb
