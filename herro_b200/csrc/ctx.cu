@@ -1176,7 +1176,9 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
     // `launch_targets` is shared by the submitting threads: each stages launch_targets / n_threads targets per launch,
     // so the targets in flight (and the latency to the first launch) do not grow with the thread count
     const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
-    uint32_t thr = std::min(lt, std::max(32u, lt / ns));
+    // ... but never less than 256 targets per launch (unless launch_targets itself is smaller): ~1 300 windows is what it takes to
+    // fill 148 SMs with the one-CTA-per-window feature kernels and to amortise the ~25 launches of a batch
+    uint32_t thr = std::min(lt, std::max(256u, lt / ns));
     // slow start: with several submitting threads, the first batches of each are small (64, 128, 256, ... targets) so that the GPU
     // has work a few milliseconds after the first submit instead of after a whole launch has been staged (a single submitting
     // thread keeps exact launch sizes: tests and the isolated launch bench.py times rely on them)

@@ -483,6 +483,7 @@ int launch_forward_chunk(const BatchView& b, const FwdWeights& wt, uint32_t n0, 
             FfnArgs fa{ws.Hhi, ws.Hlo, (const __nv_bfloat16*)ly.s_1.hi, (const __nv_bfloat16*)ly.s_1.lo,
                        (const __nv_bfloat16*)ly.s_2.hi, (const __nv_bfloat16*)ly.s_2.lo, ly.b1, ly.b2, ws.X, ng, nb, ws.Hhi, ws.Hlo,
                        (uint32_t)F, (uint32_t)(T / 128)};
+            fa.store_x = (l + 1 < wt.layers) ? 1 : 0;
             if (oproj_in_ffn(wt)) {
                 fa.Wohi = (const __nv_bfloat16*)ly.s_o.hi; fa.Wolo = (const __nv_bfloat16*)ly.s_o.lo;
                 fa.bo = ly.bo; fa.ln2_g = ly.ln2_g; fa.ln2_b = ly.ln2_b;

@@ -69,6 +69,7 @@ struct FfnArgs {  // k_ffn_ws: fused FFN for C == 128, F == 512
     // X += O · Wo^T + bo, H = LayerNorm(X; ln2) on chip.  Wohi == nullptr: unfused (H is read as given).
     const __nv_bfloat16 *Wohi = nullptr, *Wolo = nullptr;  // [128][128]
     const float *bo = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    int store_x = 1;  // 0: do not write the updated residual stream back (last layer: only LayerNorm(X) is consumed)
 };
 cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st);
 struct QkvAttnArgs {  // k_qkv_attn_ws: QKV projection + read-axis attention for C == 128, 4 heads

@@ -742,8 +742,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                     tmem_ld32(tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, xr);
 #pragma unroll
                     for (int jj = 0; jj < 32; jj++) x[c0 + jj] = __uint_as_float(v[jj]) + s_b2[ch + c0 + jj] + __uint_as_float(xr[jj]);
-                    warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
-                    warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
+                    if (g.store_x) {  // the residual stream is dead after the last layer: only its LayerNorm is consumed
+                        warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                        warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
+                    }
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
 #pragma unroll
                         for (int jj = 0; jj < 16; jj++)
                             x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_b2[ch + c0 + h * 16 + jj] + rv[jj];
-                        warp_store_f32x16(stg, lane, xblk + c0 + h * 16, BN, x + c0 + h * 16);
+                        if (g.store_x) warp_store_f32x16(stg, lane, xblk + c0 + h * 16, BN, x + c0 + h * 16);
                     }
                 }
             }
