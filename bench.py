@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--feature-threads", type=int, default=4, help="reference -t: host threads submitting targets")
+    ap.add_argument("--e2e-launch-targets", type=int, default=4000, help="hb_options.launch_targets in the e2e regions (shared by the feature "
+                    "threads: each hands over launch_targets / threads targets per device launch)")
     ap.add_argument("--host-windowing", action="store_true", help="e2e region submits host-computed OverlapWindows (hb_submit_target) instead of raw alignments")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU legs (cpu_baseline / --impl reference); 0 = all host threads")
     return ap.parse_args()
@@ -327,6 +329,7 @@ def main():
     win_timed = harness.windowing(t_t0, t_t1, wthr)
     t_windowing = time.time() - t0
 
+    ctx.set_launch_targets(max(lt, args.e2e_launch_targets))
     harness.run(t_w0, t_w1, nthr, win_warm)     # warm-up steps through the same path as the timed ones
     harness.run(t_w0, min(t_w1, t_w0 + 2 * lt), nthr, None)
     ctx.replay_last_launch(1)
@@ -355,6 +358,7 @@ def main():
     # roofline (in the pipelined region the lanes overlap, so per-kernel times there include the other lanes' kernels), and it
     # is the launch the HBM-resident replay re-runs
     ctx.reset_stats()
+    ctx.set_launch_targets(lt)
     ctx.set_kernel_timing(True)
     harness.run(cut[n_steps - 1], cut[n_steps], 1, harness.windowing(cut[n_steps - 1], cut[n_steps], wthr))  # same entry as `e2e`
     st_full = ctx.stats()
@@ -434,7 +438,7 @@ def main():
             "metric": METRIC, "value": bases_dev / t_dev, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8 pileup/consensus + f32 forward", "data": "synthetic",
-            "config": {"workload": workload, "job_targets": n_job, "targets_per_step": S, "targets_per_step_per_rank": lt,
+            "config": {"workload": workload, "job_targets": n_job, "targets_per_step": S, "targets_per_step_per_rank": lt, "e2e_launch_targets": max(lt, args.e2e_launch_targets),
                        "windows_per_step_rank0": st_full["windows"], "supported_positions_per_step_rank0": st_full["supported"],
                        "sharding": (f"read-id shard of one read set over {world} GPUs (shard.shard_targets: contiguous, balanced by windows), "
                                     f"read store replicated, no collective") if world > 1 else "single GPU",

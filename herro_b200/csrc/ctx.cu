@@ -902,8 +902,15 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) 
     {
         size_t* h = ctx->cap_hint;
         const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
-        for (int i = 0; i < 5; i++)
-            if (cur[i] > h[i]) h[i] = cur[i] + cur[i] / 4 + 64;
+        // Slow start makes the first batches smaller than a steady-state one: scale a batch of at least 32 targets (a fair sample
+        // of the per-target sizes) up to the full hand-over size, so that the pool is pinned once at its final size.
+        const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
+        const size_t full = std::min(lt, std::max(256u, lt / ns));
+        const double scale = (cur[0] >= 32 && cur[0] < full) ? (double)full / (double)cur[0] : 1.0;
+        for (int i = 0; i < 5; i++) {
+            const size_t want = (size_t)((double)cur[i] * scale);
+            if (want > h[i]) h[i] = want + want / 4 + 64;
+        }
     }
     if (ctx->queue.size() >= 2) {
         const auto t0 = std::chrono::steady_clock::now();
