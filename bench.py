@@ -330,7 +330,10 @@ def main():
     t_windowing = time.time() - t0
 
     ctx.set_launch_targets(max(lt, args.e2e_launch_targets))
-    harness.run(t_w0, t_w1, nthr, win_warm)     # warm-up steps through the same path as the timed ones
+    # warm-up: once from a single thread (hands over whole launches: every pinned / device pool reaches at least its steady-state
+    # size whatever the length of the warm-up), then through the same multi-threaded path as the timed steps
+    harness.run(t_w0, t_w1, 1, win_warm)
+    harness.run(t_w0, t_w1, nthr, win_warm)
     harness.run(t_w0, min(t_w1, t_w0 + 2 * lt), nthr, None)
     ctx.replay_last_launch(1)
     ctx.reset_stats()

@@ -258,40 +258,61 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
     for (uint32_t i = tid; i < (W >> 5) + 2; i += 256) { sup2[i] = 0; s_t[i] = extract32(tw, win.tstart + i * 32); }
     __syncthreads();
 
+    // Both walks are bound by dependent-load latency (column descriptor -> op words -> query words).  Two levels of software
+    // pipelining take the first two links off the critical path: the next column's descriptors are fetched while the current
+    // column is walked, and a lane's next op words while its current op is compared.
+    struct ColCtx { uint32_t owi, op_base, nops, t_first; QView qv; };
+    const uint32_t* __restrict__ g_kl = b.op_kl;
+    const uint32_t* __restrict__ g_t = b.op_t;
+    const uint32_t* __restrict__ g_q = b.op_q;
+    auto load_col = [&](uint32_t c) {
+        ColCtx x;
+        x.owi = cand[c];  // order is irrelevant for counting
+        const DevOW ow = b.ow[x.owi];
+        x.qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
+        x.nops = b.ow_nops[x.owi];
+        x.op_base = ow.op_base;
+        x.t_first = ow.tstart - win.tstart;
+        return x;
+    };
     // ---- walk A: coverage / gap difference array and the mismatching bases of every column
-    for (uint32_t c = warp; c < n1; c += 8) {
-        const uint32_t owi = cand[c];  // order is irrelevant for counting
-        const DevOW ow = b.ow[owi];
-        const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
-        const uint32_t nops = b.ow_nops[owi];
-        if (lane == 0) {  // the column covers [p_first, p_end): every position there is an M or a D cell
-            atomicAdd(&dcg[ow.tstart - win.tstart], 1u);
-            atomicAdd(&dcg[b.ow_tend[owi]], 0xffffffffu);
-        }
-        for (uint32_t k = lane; k < nops; k += 32) {
-            // the three op words are independent loads: issue them together (this loop is bound by load latency)
-            const uint32_t kl = b.op_kl[ow.op_base + k], t0 = b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
-            const uint32_t kind = kl & 3u, eff = kl >> 2;
-            if (kind == OP_I) continue;
-            if (kind == OP_D) {
-                atomicAdd(&dcg[t0], 0x10000u);
-                atomicAdd(&dcg[t0 + eff], 0xffff0000u);
-                continue;
+    {
+        ColCtx nxt{};
+        if ((uint32_t)warp < n1) nxt = load_col(warp);
+        for (uint32_t c = warp; c < n1; c += 8) {
+            const ColCtx cur = nxt;
+            if (c + 8 < n1) nxt = load_col(c + 8);
+            if (lane == 0) {  // the column covers [p_first, p_end): every position there is an M or a D cell
+                atomicAdd(&dcg[cur.t_first], 1u);
+                atomicAdd(&dcg[b.ow_tend[cur.owi]], 0xffffffffu);
             }
-            uint64_t qc_next = qv.chunk(q0);
-            for (uint32_t i = 0; i < eff; i += 32) {
-                const uint32_t p = t0 + i;
-                // target chunk from the staged window: 32 bases at window-relative position p
-                const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
-                const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
-                const uint64_t qc = qc_next;
-                if (i + 32 < eff) qc_next = qv.chunk(q0 + i + 32);  // next chunk's words in flight while this one's mismatches are counted
-                uint64_t mm = mismatch_groups(tc, qc, eff - i);
-                while (mm) {
-                    const int g2 = __ffsll((long long)mm) - 1;  // bit index 2g
-                    mm &= mm - 1;
-                    const uint32_t cd = (uint32_t)(qc >> g2) & 3u;
-                    atomicAdd((cd & 2u) ? &cnt_gt[p + (g2 >> 1)] : &cnt_ac[p + (g2 >> 1)], (cd & 1u) ? 0x10000u : 1u);
+            uint32_t kl_n = 0, t0_n = 0, q0_n = 0;
+            if ((uint32_t)lane < cur.nops) { kl_n = __ldg(g_kl + cur.op_base + lane); t0_n = __ldg(g_t + cur.op_base + lane); q0_n = __ldg(g_q + cur.op_base + lane); }
+            for (uint32_t k = lane; k < cur.nops; k += 32) {
+                const uint32_t kl = kl_n, t0 = t0_n, q0 = q0_n;
+                if (k + 32 < cur.nops) { kl_n = __ldg(g_kl + cur.op_base + k + 32); t0_n = __ldg(g_t + cur.op_base + k + 32); q0_n = __ldg(g_q + cur.op_base + k + 32); }
+                const uint32_t kind = kl & 3u, eff = kl >> 2;
+                if (kind == OP_I) continue;
+                if (kind == OP_D) {
+                    atomicAdd(&dcg[t0], 0x10000u);
+                    atomicAdd(&dcg[t0 + eff], 0xffff0000u);
+                    continue;
+                }
+                uint64_t qc_next = cur.qv.chunk(q0);
+                for (uint32_t i = 0; i < eff; i += 32) {
+                    const uint32_t p = t0 + i;
+                    // target chunk from the staged window: 32 bases at window-relative position p
+                    const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
+                    const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
+                    const uint64_t qc = qc_next;
+                    if (i + 32 < eff) qc_next = cur.qv.chunk(q0 + i + 32);  // next chunk's words in flight while this one's mismatches are counted
+                    uint64_t mm = mismatch_groups(tc, qc, eff - i);
+                    while (mm) {
+                        const int g2 = __ffsll((long long)mm) - 1;  // bit index 2g
+                        mm &= mm - 1;
+                        const uint32_t cd = (uint32_t)(qc >> g2) & 3u;
+                        atomicAdd((cd & 2u) ? &cnt_gt[p + (g2 >> 1)] : &cnt_ac[p + (g2 >> 1)], (cd & 1u) ? 0x10000u : 1u);
+                    }
                 }
             }
         }
@@ -343,30 +364,33 @@ __global__ void __launch_bounds__(256) k_pass1(BatchView b) {
     // ---- walk B: per-column matches on supported base rows; '.'/gap cells count as mismatches (H1),
     //      hence d = S - n for every column of the window.
     if (S > 0) {
+        ColCtx nxt{};
+        if ((uint32_t)warp < n1) nxt = load_col(warp);
         for (uint32_t c = warp; c < n1; c += 8) {
-            const uint32_t owi = cand[c];
-            const DevOW ow = b.ow[owi];
-            const QView qv = make_qview(b.rs, b.ovl[ow.ovl], ow);
-            const uint32_t nops = b.ow_nops[owi];
+            const ColCtx cur = nxt;
+            if (c + 8 < n1) nxt = load_col(c + 8);
             uint32_t n = 0;
-            for (uint32_t k = lane; k < nops; k += 32) {
-                const uint32_t kl = b.op_kl[ow.op_base + k];
+            uint32_t kl_n = 0, t0_n = 0, q0_n = 0;
+            if ((uint32_t)lane < cur.nops) { kl_n = __ldg(g_kl + cur.op_base + lane); t0_n = __ldg(g_t + cur.op_base + lane); q0_n = __ldg(g_q + cur.op_base + lane); }
+            for (uint32_t k = lane; k < cur.nops; k += 32) {
+                const uint32_t kl = kl_n, t0 = t0_n, q0 = q0_n;
+                if (k + 32 < cur.nops) { kl_n = __ldg(g_kl + cur.op_base + k + 32); t0_n = __ldg(g_t + cur.op_base + k + 32); q0_n = __ldg(g_q + cur.op_base + k + 32); }
                 if ((kl & 3u) != OP_M) continue;
-                const uint32_t eff = kl >> 2, t0 = b.op_t[ow.op_base + k], q0 = b.op_q[ow.op_base + k];
+                const uint32_t eff = kl >> 2;
                 for (uint32_t i = 0; i < eff; i += 32) {
                     const uint32_t p = t0 + i;
                     const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
                     const uint64_t sc = sh ? ((sup2[wi] >> sh) | (sup2[wi + 1] << (64u - sh))) : sup2[wi];
                     if (!sc) continue;  // no supported position among these 32: the query words are not even fetched
                     const uint64_t tc = sh ? ((s_t[wi] >> sh) | (s_t[wi + 1] << (64u - sh))) : s_t[wi];
-                    const uint64_t mm = mismatch_groups(tc, qv.chunk(q0 + i), eff - i);
+                    const uint64_t mm = mismatch_groups(tc, cur.qv.chunk(q0 + i), eff - i);
                     n += (uint32_t)__popcll(sc & valid_groups(eff - i) & ~mm);
                 }
             }
             n = warp_sum(n);
             if (lane == 0) {
-                atomicAdd(&b.ovl_n[ow.ovl], n);
-                atomicAdd(&b.ovl_tot[ow.ovl], S);
+                atomicAdd(&b.ovl_n[b.ow[cur.owi].ovl], n);
+                atomicAdd(&b.ovl_tot[b.ow[cur.owi].ovl], S);
             }
         }
     }
