@@ -1150,28 +1150,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
     __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
     __shared__ __align__(16) float s_bias[BN], s_lng[BN], s_lnb[BN];
     __shared__ float s_red[2][2][BM];                    // [item parity][column half][row]: LayerNorm partial sums
-    // A-operand synthesis tables: the 16 bf16 features of a token (one-hot slot), and (q_hi | q_lo << 16) of a quality byte
-    __shared__ __align__(16) uint4 s_lut[13][2];
-    __shared__ uint32_t s_qlut[256];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < BN) {
         s_bias[tid] = g.bias[tid];
         s_lng[tid] = g.out_hi ? g.ln_g[tid] : 1.f;
         s_lnb[tid] = g.out_hi ? g.ln_b[tid] : 0.f;
-    }
-    if (tid < 256) {
-        const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
-        const float q = __fsub_rn(__fmul_rn((float)tid, QS), QO);
-        const __nv_bfloat16 qh = __float2bfloat16_rn(q);
-        const __nv_bfloat16 ql = __float2bfloat16_rn(q - __bfloat162float(qh));
-        s_qlut[tid] = (uint32_t)__bfloat16_as_ushort(qh) | ((uint32_t)__bfloat16_as_ushort(ql) << 16);
-    }
-    if (tid < 13) {
-        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tid < 11) w[tid >> 1] = (tid & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0 in feature slot `tid`
-        s_lut[tid][0] = make_uint4(w[0], w[1], w[2], w[3]);
-        s_lut[tid][1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     for (int i = tid; i < 32 * BN; i += S_THREADS) {
         const int r = i >> 7, c = i & 127;
@@ -1217,7 +1201,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                     tma_load_2d(smem_u32(sA) + BM * 128, &tmWhi, &full_bar[s], (int)(kb * BK), 0);
                     tma_load_2d(smem_u32(sA) + BM * 128 + BN * 128, &tmWlo, &full_bar[s], (int)(kb * BK), 0);
                 }
-                // ---- A k-block: 4 taps x 16 features of this row, looked up (one-hot token slot | quality columns)
+                // ---- A k-block: 4 taps x 16 features of this row, synthesised arithmetically: bf16 1.0 in the token's one-hot slot
+                //      (features 0..10; '.' has a slot, the pad token 11 and rows outside the reference batch are all zero) and the
+                //      normalised quality as (q_hi, q_lo) in features 11, 12.  (Round 1 looked both up in shared-memory tables: the 256-entry
+                //      quality table is indexed by data, i.e. 3-4-way bank conflicts on every look-up; ncu counted 43 M conflicts per launch.)
                 uint32_t tk[4], qq[4];
 #pragma unroll
                 for (int tl = 0; tl < 4; tl++) {
@@ -1228,15 +1215,23 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 }
 #pragma unroll
                 for (int tl = 0; tl < 4; tl++) {
-                    const uint32_t idx = min(tk[tl], 12u);  // 0xff (row outside the reference batch / pad read) -> all zero
-                    uint4 w0 = s_lut[idx][0], w1 = s_lut[idx][1];
-                    if (idx < 12u) {
-                        const uint32_t qw = s_qlut[qq[tl]];
-                        w1.y |= qw << 16;      // feature 11 = q_hi
-                        w1.z |= qw >> 16;      // feature 12 = q_lo
+                    const uint32_t tok = tk[tl];
+                    const bool live = tok < 12u;                       // 0xff: contributes nothing (not even its quality)
+                    const uint32_t one = (tok & 1u) ? 0x3f800000u : 0x00003f80u;
+                    const uint32_t slot = tok < 11u ? (tok >> 1) : 8u;  // word holding the one-hot 1.0; 8 = none
+                    uint32_t w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) w[k] = (slot == (uint32_t)k) ? one : 0u;
+                    if (live) {
+                        const float QS = (float)(2.0 / 93.0), QO = (float)(2.0 * 33.0 / 93.0 + 1.0);  // src/inference.rs:19-21
+                        const float q = __fsub_rn(__fmul_rn((float)qq[tl], QS), QO);
+                        const __nv_bfloat16 qh = __float2bfloat16_rn(q);
+                        const __nv_bfloat16 ql = __float2bfloat16_rn(q - __bfloat162float(qh));
+                        w[5] |= (uint32_t)__bfloat16_as_ushort(qh) << 16;  // feature 11 = q_hi
+                        w[6] |= (uint32_t)__bfloat16_as_ushort(ql);        // feature 12 = q_lo
                     }
-                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl) ^ (p & 7)) << 4)) = w0;
-                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl + 1) ^ (p & 7)) << 4)) = w1;
+                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl) ^ (p & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *(uint4*)(sA + (uint32_t)p * 128u + (uint32_t)(((2 * tl + 1) ^ (p & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&full_bar[s]);
