@@ -421,9 +421,11 @@ def main():
                 break
             except Exception:
                 pass
-        t_top = traffic.get(KERNEL_OF[top], {}).get("dram_bytes_per_launch")
-        tnote = (f"from file profiles/{traffic_src} (ncu --set full capture of {traffic.get('_capture', 'another run')}; not measured in this run, "
-                 f"scale by launch size)") if t_top is not None else None
+        import re
+        traffic = {re.sub(r"^void |<.*", "", k): v for k, v in traffic.items()}   # "void k_ffn_ws<1>" -> "k_ffn_ws"
+        t_top = traffic[KERNEL_OF[top]].get("dram_bytes_per_launch") if isinstance(traffic.get(KERNEL_OF[top]), dict) else None
+        tnote = (f"from file profiles/{traffic_src} ({traffic.get('_note', 'ncu --set full capture of another run')}); not measured in this run"
+                 ) if t_top is not None else None
         if top == "pileup":
             roof = {"kernel": "k_pileup (" + DESCR[top] + ")", "bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": pile_gbs / hbm_peak, "traffic": t_top, "traffic_note": tnote, "peak_source": peak_src,
