@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--feature-threads", type=int, default=4, help="reference -t: host threads submitting targets")
+    ap.add_argument("--feature-threads", type=int, default=8, help="reference -t: host threads submitting targets (4 threads stage ~40 targets/ms, about what one B200 consumes)")
     ap.add_argument("--e2e-launch-targets", type=int, default=4000, help="hb_options.launch_targets in the e2e regions (shared by the feature "
                     "threads: each hands over launch_targets / threads targets per device launch)")
     ap.add_argument("--host-windowing", action="store_true", help="e2e region submits host-computed OverlapWindows (hb_submit_target) instead of raw alignments")

@@ -1110,7 +1110,8 @@ int prepare_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overl
     for (uint32_t w = 0; w < n_windows; w++) P.win_begin[w + 1] += P.win_begin[w];
     // bucket by window, keeping push order (= alignment order) inside each
     P.ow.resize(n_ow);
-    std::vector<uint32_t> fill(P.win_begin.begin(), P.win_begin.end() - 1);
+    thread_local std::vector<uint32_t> fill;  // scratch reused across calls: no allocation per target
+    fill.assign(P.win_begin.begin(), P.win_begin.end() - 1);
     for (uint32_t i = 0; i < n_ow; i++) {
         const hb_overlap_window& s = ow[i];
         P.ow[fill[s.window_idx]++] = DevOW{s.overlap_idx, s.window_idx, s.tstart, s.qstart, s.qend, s.cigar_start_idx,
@@ -1364,7 +1365,8 @@ int hb_upload_reads(hb_ctx* ctx, uint32_t n_reads, const uint64_t* const* seq_wo
 int hb_submit_target(hb_ctx* ctx, uint32_t rid, uint32_t n_windows, const hb_overlap* ovl, uint32_t n_ovl,
                      const hb_overlap_window* ow, uint32_t n_ow) {
     if (!ctx) return HB_ERR_ARG;
-    PreparedTarget P;
+    thread_local PreparedTarget P;  // its vectors keep their capacity from target to target
+    P.raw = false;
     t_err_sink = nullptr;
     std::string local_err;
     {   // validation errors are written to a local string first: ctx->err is shared between feature threads
@@ -1396,12 +1398,13 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
     // Device windowing (windowing_dev.cu): the host only lays out which (alignment, window) pairs exist — a function of the PAF
     // coordinates — and ships the CIGARs; a CIGAR that is malformed or disagrees with its coordinates fails this target at
     // hb_poll_corrected (HB_ERR_INPUT) instead of here.
-    PreparedTarget P;
+    thread_local PreparedTarget P;  // scratch reused across calls
+    thread_local std::vector<uint32_t> first, fill;
     P.raw = true;
     P.rid = rid; P.n_windows = n_windows; P.len = ctx->read_len[rid];
     P.win_begin.assign(n_windows + 1, 0);
     P.aln_now.assign(n_ovl, 0);
-    std::vector<uint32_t> first(n_ovl, 0);
+    first.assign(n_ovl, 0);
     uint64_t cb = 0;
     for (uint32_t i = 0; i < n_ovl; i++) {
         if (ovl[i].tid != rid) return fail_locked(HB_ERR_ARG, "overlap.tid != rid (alignments must be grouped by target)");
@@ -1419,7 +1422,7 @@ int hb_submit_alignments(hb_ctx* ctx, uint32_t rid, const hb_overlap* ovl, uint3
     for (uint32_t w = 0; w < n_windows; w++) P.win_begin[w + 1] += P.win_begin[w];
     P.cig_bytes = cb;
     P.ow.resize(P.win_begin[n_windows]);
-    std::vector<uint32_t> fill(P.win_begin.begin(), P.win_begin.end() - 1);
+    fill.assign(P.win_begin.begin(), P.win_begin.end() - 1);
     for (uint32_t i = 0; i < n_ovl; i++)  // alignment order inside every window = the reference's push order
         for (uint32_t w = first[i]; w < first[i] + P.aln_now[i]; w++) P.ow[fill[w]++] = DevOW{i, w, 0, 0, 0, 0, 0, 0, 0, 0};
     return stage_target(ctx, P, ovl, n_ovl);
