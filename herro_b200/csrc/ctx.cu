@@ -892,7 +892,8 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
 
 // Hand a staged batch to the launch worker (lock held); `b` is left empty (no capacity).
 // Back-pressure: at most 2 batches wait in the queue.
-void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) {
+void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b, uint32_t full_targets = 0) {
+    // full_targets != 0: this batch was cut short by the slow start; a steady-state hand-over will hold that many targets
     if (b.tgt.empty()) return;
     // capacity hint for staging batches: the largest arrays handed over so far plus a margin, so that pinned memory is
     // allocated once per batch object and then recycled.  (No extrapolation from partial batches: a two-target
@@ -902,11 +903,11 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b) 
     {
         size_t* h = ctx->cap_hint;
         const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
-        // Slow start makes the first batches smaller than a steady-state one: scale a batch of at least 32 targets (a fair sample
-        // of the per-target sizes) up to the full hand-over size, so that the pool is pinned once at its final size.
-        const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
-        const size_t full = std::min(lt, std::max(256u, lt / ns));
-        const double scale = (cur[0] >= 32 && cur[0] < full) ? (double)full / (double)cur[0] : 1.0;
+        // Slow start makes the first batches smaller than a steady-state one: scale such a batch (at least 32 targets, a fair sample
+        // of the per-target sizes) up to the full hand-over size, so that the pool is pinned once at its final size.  Only batches
+        // that the slow start cut are scaled (never a flush remainder, never against an "everything in one launch" launch_targets),
+        // and by at most 16x.
+        const double scale = (full_targets && cur[0] >= 32 && cur[0] < full_targets) ? std::min(16.0, (double)full_targets / (double)cur[0]) : 1.0;
         for (int i = 0; i < 5; i++) {
             const size_t want = (size_t)((double)cur[i] * scale);
             if (want > h[i]) h[i] = want + want / 4 + 64;
@@ -1190,10 +1191,11 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
     // slow start: with several submitting threads, the first batches of each are small (64, 128, 256, ... targets) so that the GPU
     // has work a few milliseconds after the first submit instead of after a whole launch has been staged (a single submitting
     // thread keeps exact launch sizes: tests and the isolated launch bench.py times rely on them)
+    const uint32_t full_thr = thr;
     if (ns >= 2 && slot->handed < 4) thr = std::min(thr, 64u << slot->handed);
     if (slot->batch.tgt.size() >= thr) {
         std::unique_lock<std::mutex> lk(ctx->mu);
-        enqueue_batch(ctx, lk, slot->batch);
+        enqueue_batch(ctx, lk, slot->batch, thr < full_thr ? full_thr : 0u);
         slot->handed++;
     }
     return HB_OK;
