@@ -145,7 +145,9 @@ struct PinVec {
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
     bool reserve(size_t want) {
         if (want <= cap) return true;
+        if (want * sizeof(T) > ((size_t)24 << 30)) return false;  // a staging array of > 24 GB is a sizing bug, not a workload: fail, do not pin
         size_t ncap = (n == 0) ? std::max<size_t>(want, 4096) : std::max<size_t>(want * 2, 4096);
+        if (ncap * sizeof(T) > ((size_t)24 << 30)) ncap = want;
         AllocScope as_("pinned(staging)", ncap * sizeof(T));
         T* np = nullptr;
         int cur = -1;
