@@ -24,6 +24,7 @@
 // Two TMEM accumulators (2 x 128 columns) let the epilogue of item i overlap the MMAs of i+1.
 // Work items (m_tile, n_chunk) are dealt round-robin so CTAs working on the same m_tile share
 // its A tile in L2.
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -75,6 +76,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                  "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
                  : "memory");
 }
+// TMA store of one SWIZZLE_128B [128 rows x 64 bf16] shared-memory tile into a 2-D tensor (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c_inner, int c_row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)tm), "r"(src), "r"(c_inner),
+                 "r"(c_row)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be overwritten
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // pull a line towards L2 ahead of the (latency-exposed) row-owner loads of an epilogue
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -457,22 +467,32 @@ constexpr int FFN_STAGES = 2;  // 2 x 64 KB operand tiles + 2 x 32 KB ring = 192
 // This removes the HBM-bound out-projection kernel (it re-read and re-wrote the fp32 residual stream: 256 KB per 128-token
 // tile and layer).  Cost: accO is single-buffered (its second buffer holds X'), so the next tile's P0 waits for this tile's
 // final epilogue to drain the accumulator.
+// Per-role timeline of two tiles of block 0 (clock64), compiled in with -DHB_FFN_TRACE and printed by ffn_tc on its 25th call:
+// how the numbers in DESIGN.md 4.3 (who waits for whom inside a tile) were obtained.  Not part of the product build.
+#ifdef HB_FFN_TRACE
+__device__ unsigned long long hb_ffn_trace[3][2][64];  // [role: 0 MMA, 1 epilogue thread 0, 2 producer][tile 10/11][event]
+#define TR(role, k) do { if (blockIdx.x == 0 && (n_done == 10 || n_done == 11)) hb_ffn_trace[role][n_done - 10][k] = clock64(); } while (0)
+#else
+#define TR(role, k) do { } while (0)
+#endif
 template <bool FUSE_O>
 __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid_constant__ CUtensorMap tmHhi,
                                                         const __grid_constant__ CUtensorMap tmHlo, const __grid_constant__ CUtensorMap tmW1hi,
                                                         const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmW2hi,
                                                         const __grid_constant__ CUtensorMap tmW2lo, const __grid_constant__ CUtensorMap tmWohi,
-                                                        const __grid_constant__ CUtensorMap tmWolo) {
+                                                        const __grid_constant__ CUtensorMap tmWolo, const __grid_constant__ CUtensorMap tmOhi,
+                                                        const __grid_constant__ CUtensorMap tmOlo) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
     uint8_t* sA2 = sA1 + FFN_A_BYTES;               // relu(hidden chunk) tile, same layout
     uint8_t* ring = sA2 + FFN_A_BYTES;              // FFN_STAGES x FFN_RING_BYTES
-    __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full, a2_empty,
+    __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full[2], a2_empty[2],
         o_full[2], o_empty[2], y_full, h_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ volatile uint32_t s_prog;  // tiles the producer lane has started (paces the L2 prefetch of the residual rows)
     __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN], s_bo[BN], s_ln2g[BN], s_ln2b[BN];
-    __shared__ float s_red[2][2][BM];  // [tile parity][column half][row]: LayerNorm partial sums
+    __shared__ float s_red[2][2][BM], s_red2[2][2][BM];  // [slot][column half][row]: LayerNorm partial sums / squared deviations
     __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -481,12 +501,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
+        s_prog = 0;
         for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&a1_full, 1); mbar_init(&a1_empty, 1);
-        mbar_init(&a2_full, G_EPI); mbar_init(&a2_empty, 1);
         mbar_init(&y_full, 1); mbar_init(&h_full, G_EPI);
         for (int a = 0; a < 2; a++) {
             mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], G_EPI);
+            mbar_init(&a2_full[a], G_EPI); mbar_init(&a2_empty[a], 1);  // per k-block of A2
             mbar_init(&o_full[a], 1); mbar_init(&o_empty[a], G_EPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -502,17 +523,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
 
     if (warp == G_PROD_WARP) {
         // =============================== producer: one lane issues the TMA copies ===============================
+        // The other lanes pull the residual rows E0 will add one tile from now towards L2 (fp32 X comes from DRAM: with 4
+        // dependent rounds of loads per thread, DRAM latency was 4.9 k cycles of E0 with the tensor pipe idle).
+        if (FUSE_O && lane != 0) {
+            uint32_t n = 0;
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n++) {
+                while ((int)(n - s_prog) > 1) __nanosleep(1000);  // at most one tile ahead of the tile lane 0 is loading
+                for (int i = lane - 1; i < BM * 4; i += 31) prefetch_l2((const char*)(g.X + (size_t)tile * BM * BN) + (size_t)i * 128);
+            }
+        }
         if (lane == 0) {
             uint32_t it_stage = 0, n_done = 0;
-            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+            // H tile (resident for a whole tile): 2 k-blocks x (hi, lo).  Tile t+1's is requested as soon as F1(3) of tile t has
+            // released the buffer (behind the stages of step 6, whose ring slots F1(3) frees as well), not after the producer has
+            // queued all of tile t's weights: it is the first thing tile t+1 needs.
+            auto load_a1 = [&](uint32_t tile, uint32_t n) {
                 const int m0 = (int)(tile * BM);
-                // ---- H tile (resident for the whole tile): 2 k-blocks x (hi, lo)
-                mbar_wait(&a1_empty, (n_done & 1) ^ 1);
+                mbar_wait(&a1_empty, (n & 1) ^ 1);
                 mbar_arrive_expect_tx(&a1_full, FFN_A_BYTES);
                 for (int kb = 0; kb < 2; kb++) {
                     tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128), &tmHhi, &a1_full, kb * BK, m0);
                     tma_load_2d(smem_u32(sA1) + kb * (2 * BM * 128) + BM * 128, &tmHlo, &a1_full, kb * BK, m0);
                 }
+            };
+            if (blockIdx.x < g.m_tiles) load_a1(blockIdx.x, 0);
+            for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                s_prog = n_done;
                 if (FUSE_O) {  // Wo: 2 k-block tiles, ahead of the FFN weights
                     for (int kb = 0; kb < 2; kb++, it_stage++) {
                         const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
@@ -527,9 +563,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 for (int st = 0; st < 8; st++) {
                     int is2, c;
                     ffn_step(st, is2, c);
+                    if (st == 7 && tile + gridDim.x < g.m_tiles) load_a1(tile + gridDim.x, n_done + 1);
                     for (int kb = 0; kb < 2; kb++, it_stage++) {
                         const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        TR(2, 4 * st + 2 * kb);
                         mbar_wait(&empty_bar[s], ph ^ 1);
+                        TR(2, 4 * st + 2 * kb + 1);
                         const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
                         mbar_arrive_expect_tx(&full_bar[s], FFN_RING_BYTES);
                         // F1(c): rows = hidden units c*128.., K = C;   F2(c): rows = outputs, K-columns = hidden units c*128..
@@ -543,11 +582,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
     } else if (warp == G_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            uint32_t it_stage = 0, n_done = 0, nf[2] = {0, 0}, na2 = 0;
+            uint32_t it_stage = 0, n_done = 0, nf[2] = {0, 0}, na2 = 0;  // na2: A2 k-block generations consumed
             const uint32_t a1b = smem_u32(sA1), a2b = smem_u32(sA2);
             for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
                 const uint32_t oacc = FUSE_O ? 0u : (n_done & 1);
+                TR(0, 0);
                 mbar_wait(&a1_full, n_done & 1);
+                TR(0, 1);
                 if (FUSE_O) {
                     // ---- P0: accO = O · Wo^T (the previous tile's final epilogue must have drained accO)
                     mbar_wait(&o_empty[0], (n_done & 1) ^ 1);
@@ -570,28 +611,33 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                         umma_commit(&empty_bar[s]);
                     }
                     umma_commit(&y_full);
-                    mbar_wait(&h_full, n_done & 1);  // E0 has replaced the O tile by H = LN2(X') in shared memory
+                    TR(0, 2);
+                    mbar_wait(&h_full, n_done & 1);
+                    TR(0, 3);  // E0 has replaced the O tile by H = LN2(X') in shared memory
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 for (int st = 0; st < 8; st++) {
                     int is2, c;
                     ffn_step(st, is2, c);
                     uint32_t tmem_d, abase;
+                    TR(0, 4 + 4 * st);
                     if (!is2) {
                         const uint32_t j = c & 1;
                         mbar_wait(&f_empty[j], (nf[j] & 1) ^ 1);  // epilogue has drained accF[j]
                         tmem_d = tmem_base + j * BN;
                         abase = a1b;
                     } else {
-                        mbar_wait(&a2_full, na2 & 1);             // E1(c) has written the hidden chunk
                         if (!FUSE_O && c == 0) mbar_wait(&o_empty[oacc], ((n_done >> 1) & 1) ^ 1);
                         tmem_d = tmem_base + 2 * BN + oacc * BN;
                         abase = a2b;
                     }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    TR(0, 5 + 4 * st);
                     for (int kb = 0; kb < 2; kb++, it_stage++) {
                         const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
+                        if (is2) mbar_wait(&a2_full[kb], na2 & 1);  // E1(c) has written this k-block of the hidden chunk
                         mbar_wait(&full_bar[s], ph);
+                        TR(0, 6 + 4 * st + kb);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t sb = smem_u32(ring + (size_t)s * FFN_RING_BYTES);
                         const uint64_t dAh = make_desc(abase + kb * (2 * BM * 128)), dAl = make_desc(abase + kb * (2 * BM * 128) + BM * 128);
@@ -605,13 +651,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                             mma_bf16(tmem_d, dAh + adv, dBl + adv, 1u);
                         }
                         umma_commit(&empty_bar[s]);
+                        if (is2) umma_commit(&a2_empty[kb]);      // E1(c+1) may refill this k-block while the other one is still being read
                     }
                     if (!is2) {
                         umma_commit(&f_full[c & 1]);
                         nf[c & 1]++;
                         if (c == 3) umma_commit(&a1_empty);       // H tile no longer needed
                     } else {
-                        umma_commit(&a2_empty);
                         na2++;
                         if (c == 3) umma_commit(&o_full[oacc]);
                     }
@@ -632,11 +678,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             }
             if (FUSE_O) {
                 // ---- E0: X' = accO + bo + X (parked in TMEM), H = LN2(X') -> split bf16 -> over the O tile (A operand of FFN1)
-                float4 pre[4];
+                float4 pre[2][4];
                 float* stg = s_stage[warp];
                 const float* xblk = g.X + ((size_t)tile * BM + wq * 32) * BN + ch;
-                warp_ldg_f32x16(lane, xblk, BN, pre);  // requested before the wait for the MMAs
+                warp_ldg_f32x16(lane, xblk, BN, pre[0]);       // requested before the wait for the MMAs, two blocks ahead
+                warp_ldg_f32x16(lane, xblk + 16, BN, pre[1]);
+                if (tid == 0) TR(1, 0);
                 mbar_wait(&y_full, n_done & 1);
+                if (tid == 0) TR(1, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + 2 * BN + ch + ((uint32_t)(wq * 32) << 16);
                 const uint32_t txs = tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16);
@@ -648,8 +697,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         float rv[16];
-                        warp_xpose_f32x16(stg, lane, pre, rv);
-                        if (c0 + h * 16 + 16 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 16, BN, pre);
+                        warp_xpose_f32x16(stg, lane, pre[h], rv);
+                        if (c0 + h * 16 + 32 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 32, BN, pre[h]);
 #pragma unroll
                         for (int jj = 0; jj < 16; jj++) {
                             x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_bo[ch + c0 + h * 16 + jj] + rv[jj];
@@ -657,6 +706,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                         }
                     }
                     tmem_st32(txs + (uint32_t)c0, v);
+                }
+                if (tid == 0) {
+                    TR(1, 44);
+                    tma_store_wait_read();  // the previous tile's H tile has left A2 (the LayerNorm barriers below order E1(0)'s writes behind this)
                 }
                 float sum = 0.f;
 #pragma unroll
@@ -667,10 +720,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 float var = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < 64; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
+                s_red2[0][eh][r] = var;  // its own array: no barrier needed between the reads of the sums and this write
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                s_red[0][eh][r] = var;
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                const float rstd = rsqrtf((s_red[0][0][r] + s_red[0][1][r]) * (1.f / BN) + 1e-5f);
+                const float rstd = rsqrtf((s_red2[0][0][r] + s_red2[0][1][r]) * (1.f / BN) + 1e-5f);
+                if (tid == 0) TR(1, 45);
                 uint8_t* a1row = sA1 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
 #pragma unroll
                 for (int q8 = 0; q8 < 8; q8++) {  // 8 x 8 channels = 8 x 16-byte chunks of hi and of lo
@@ -689,22 +742,31 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of H -> tensor core
                 mbar_arrive(&h_full);
+                if (tid == 0) TR(1, 2);
             }
             for (int c = 0; c < 4; c++) {
-                // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major; this thread's 64 columns = k-block eh)
+                // ---- E1(c): relu(accF + b1) -> split bf16 -> A2 (swizzled K-major), k-block by k-block: every thread does 32 hidden
+                //      units of k-block 0, hands it to the tensor pipe, then 32 of k-block 1 - so F2(c) starts after half of E1(c) and
+                //      E1(c+1) starts after half of F2(c) (one barrier pair per k-block; with one pair per chunk the two alternated)
                 const uint32_t j = c & 1;
+                if (tid == 0) TR(1, 3 + 4 * c);
                 mbar_wait(&f_full[j], nf[j] & 1);
                 nf[j]++;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                mbar_wait(&a2_empty, (na2 & 1) ^ 1);              // F2(c-1) has finished reading A2
-                na2++;
-                const uint32_t taddr = tmem_base + j * BN + ch + ((uint32_t)(wq * 32) << 16);
-                uint8_t* a2row = sA2 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
+                if (tid == 0) TR(1, 4 + 4 * c);
+                const uint32_t taddr = tmem_base + j * BN + eh * 32 + ((uint32_t)(wq * 32) << 16);
+#pragma unroll
+                for (int kb = 0; kb < 2; kb++) {
+                    mbar_wait(&a2_empty[kb], (na2 & 1) ^ 1);      // F2(c-1) has finished reading this k-block of A2
+                    if (tid == 0 && kb == 0) TR(1, 5 + 4 * c);
+                    uint8_t* a2row = sA2 + (uint32_t)kb * (2 * BM * 128) + r * 128u;
                     uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);
-                    const float* bb = s_b1 + c * 128 + ch + c0;
+                    tmem_ld32(taddr + (uint32_t)(kb * 64), v);
+                    if (kb == 1) {  // accF[j] is drained
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&f_empty[j]);
+                    }
+                    const float* bb = s_b1 + c * 128 + kb * 64 + eh * 32;
 #pragma unroll
                     for (int q8 = 0; q8 < 4; q8++) {              // 4 x 8 hidden units = 4 x 16-byte chunks of hi and of lo
                         uint32_t hi[4], lo[4];
@@ -712,22 +774,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                         for (int e = 0; e < 8; e += 2)
                             split2(fmaxf(__uint_as_float(v[q8 * 8 + e]) + bb[q8 * 8 + e], 0.f),
                                    fmaxf(__uint_as_float(v[q8 * 8 + e + 1]) + bb[q8 * 8 + e + 1], 0.f), hi[e >> 1], lo[e >> 1]);
-                        const int cc = (c0 >> 3) + q8;            // 16-byte chunk index inside the 128-byte k-block row
-                        const uint32_t off = (uint32_t)((cc ^ (r & 7)) << 4);
+                        const uint32_t off = (uint32_t)(((eh * 4 + q8) ^ (r & 7)) << 4);
                         *(uint4*)(a2row + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *(uint4*)(a2row + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A2 -> tensor core
+                    mbar_arrive(&a2_full[kb]);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&f_empty[j]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A2 -> tensor core
-                mbar_arrive(&a2_full);
+                na2++;
+                if (tid == 0) TR(1, 6 + 4 * c);
             }
             // ---- final epilogue: X = accO + b2 + X ; LayerNorm -> split bf16 (partial sums exchanged between the halves)
             const uint32_t oacc = FUSE_O ? 0u : (n_done & 1);
             float4 pre[4];  // first residual block: requested before the wait for the last MMAs (it does not depend on them)
             if (!FUSE_O) warp_ldg_f32x16(lane, g.X + ((size_t)tile * BM + wq * 32) * BN + ch, BN, pre);
+            if (tid == 0) TR(1, 40);
             mbar_wait(&o_full[oacc], FUSE_O ? (n_done & 1) : ((n_done >> 1) & 1));
+            if (tid == 0) TR(1, 41);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + 2 * BN + oacc * BN + ch + ((uint32_t)(wq * 32) << 16);
             float x[64];
@@ -742,10 +805,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                     tmem_ld32(tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, xr);
 #pragma unroll
                     for (int jj = 0; jj < 32; jj++) x[c0 + jj] = __uint_as_float(v[jj]) + s_b2[ch + c0 + jj] + __uint_as_float(xr[jj]);
-                    if (g.store_x) {  // the residual stream is dead after the last layer: only its LayerNorm is consumed
-                        warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
-                        warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
-                    }
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
@@ -761,36 +820,58 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&o_empty[oacc]);
+            if (tid == 0) TR(1, 42);
+            if (FUSE_O && g.store_x) {  // the residual stream is dead after the last layer: only its LayerNorm is consumed
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+            }
             float sum = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) sum += x[jj];
-            const uint32_t rs_ = FUSE_O ? 1u : oacc;
+            const uint32_t rs_ = FUSE_O ? 1u : oacc;  // E0 uses s_red[0]
             s_red[rs_][eh][r] = sum;
             asm volatile("bar.sync 2, 256;" ::: "memory");
             const float mean = (s_red[rs_][0][r] + s_red[rs_][1][r]) * (1.f / BN);
             float var = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) { const float d = x[jj] - mean; var = fmaf(d, d, var); }
+            s_red2[rs_][eh][r] = var;
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            s_red[rs_][eh][r] = var;
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            const float rstd = rsqrtf((s_red[rs_][0][r] + s_red[rs_][1][r]) * (1.f / BN) + 1e-5f);
-            __nv_bfloat16* hblk = g.out_hi + ((size_t)tile * BM + wq * 32) * BN + ch;
-            __nv_bfloat16* lblk = g.out_lo + ((size_t)tile * BM + wq * 32) * BN + ch;
+            const float rstd = rsqrtf((s_red2[rs_][0][r] + s_red2[rs_][1][r]) * (1.f / BN) + 1e-5f);
+            // LayerNorm(X) -> split bf16 -> the (idle) A2 tile in the layout of an operand tile ([kb][hi|lo][128 x 128 B], swizzled) ->
+            // 4 TMA stores by one thread.  (Row-owner -> coalesced transposes through the per-warp staging buffers, 16 STS/LDS/STG
+            // round trips per thread, were 5.8 k cycles of every tile during which nothing else could use the epilogue warps.)
+            uint8_t* orow = sA2 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
 #pragma unroll
-            for (int jj = 0; jj < 64; jj += 16) {
-                uint32_t hi[8], lo[8];
+            for (int q8 = 0; q8 < 8; q8++) {
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const float a = (x[jj + e] - mean) * rstd * s_lng[ch + jj + e] + s_lnb[ch + jj + e];
-                    const float b = (x[jj + e + 1] - mean) * rstd * s_lng[ch + jj + e + 1] + s_lnb[ch + jj + e + 1];
-                    split2(a, b, hi[e >> 1], lo[e >> 1]);
+                for (int e = 0; e < 8; e += 2) {
+                    const int jj = q8 * 8 + e;
+                    const float a = (x[jj] - mean) * rstd * s_lng[ch + jj] + s_lnb[ch + jj];
+                    const float bq = (x[jj + 1] - mean) * rstd * s_lng[ch + jj + 1] + s_lnb[ch + jj + 1];
+                    split2(a, bq, hi[e >> 1], lo[e >> 1]);
                 }
-                warp_store_bf16x16((uint32_t*)stg, lane, hblk + jj, BN, hi);
-                warp_store_bf16x16((uint32_t*)stg, lane, lblk + jj, BN, lo);
+                const uint32_t off = (uint32_t)((q8 ^ (r & 7)) << 4);
+                *(uint4*)(orow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *(uint4*)(orow + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (tid == 0) {
+                const int m0 = (int)(tile * BM);
+                for (int kb = 0; kb < 2; kb++) {
+                    tma_store_2d(&tmOhi, smem_u32(sA2) + kb * (2 * BM * 128), kb * BK, m0);
+                    tma_store_2d(&tmOlo, smem_u32(sA2) + kb * (2 * BM * 128) + BM * 128, kb * BK, m0);
+                }
+                tma_store_commit();
+                if (!FUSE_O) tma_store_wait_read();  // no E0 in front of the next E1(0): wait here
+            }
+            if (!FUSE_O) asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (tid == 0) TR(1, 43);
         }
     }
+    if (tid == 0) tma_store_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == G_MMA_WARP) {
@@ -1455,17 +1536,33 @@ cudaError_t ffn_tc(const FfnArgs& a, int num_sms, cudaStream_t st) {
         configured = true;
     }
     if (a.m_tiles == 0) return cudaSuccess;
-    CUtensorMap tHh, tHl, t1h, t1l, t2h, t2l, toh, tol;
+    CUtensorMap tHh, tHl, t1h, t1l, t2h, t2l, toh, tol, tOh, tOl;
     const uint64_t T = (uint64_t)a.m_tiles * BM;
     if (!make_tmap(&tHh, a.Hhi, T, BN, BN) || !make_tmap(&tHl, a.Hlo, T, BN, BN) || !make_tmap(&t1h, a.W1hi, a.F, BN, BN) ||
         !make_tmap(&t1l, a.W1lo, a.F, BN, BN) || !make_tmap(&t2h, a.W2hi, BN, a.F, a.F) || !make_tmap(&t2l, a.W2lo, BN, a.F, a.F))
         return cudaErrorInvalidValue;
+    if (!make_tmap(&tOh, a.out_hi, T, BN, BN) || !make_tmap(&tOl, a.out_lo, T, BN, BN)) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms);
     if (a.Wohi) {
         if (!make_tmap(&toh, a.Wohi, BN, BN, BN) || !make_tmap(&tol, a.Wolo, BN, BN, BN)) return cudaErrorInvalidValue;
-        k_ffn_ws<true><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, toh, tol);
+        k_ffn_ws<true><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, toh, tol, tOh, tOl);
+#ifdef HB_FFN_TRACE
+        static int calls = 0;
+        if (++calls == 25 && a.m_tiles > 148 * 12) {
+            cudaStreamSynchronize(st);
+            static unsigned long long h[3][2][64];
+            cudaMemcpyFromSymbol(h, hb_ffn_trace, sizeof(h));
+            const unsigned long long t0 = h[0][0][0];
+            for (int r = 0; r < 3; r++)
+                for (int t = 0; t < 2; t++) {
+                    fprintf(stderr, "FFNTRACE role %d tile %d:", r, t);
+                    for (int k = 0; k < 64; k++) fprintf(stderr, " %lld", h[r][t][k] ? (long long)(h[r][t][k] - t0) : -1LL);
+                    fprintf(stderr, "\n");
+                }
+        }
+#endif
     } else {
-        k_ffn_ws<false><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, t1h, t1l);
+        k_ffn_ws<false><<<grid, G_THREADS, smem, st>>>(a, tHh, tHl, t1h, t1l, t2h, t2l, t1h, t1l, tOh, tOl);
     }
     return cudaGetLastError();
 }
