@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
     uint8_t* sA1 = smem;                            // H tile: [kb][hi|lo][128 x 128 B]
     uint8_t* sA2 = sA1 + FFN_A_BYTES;               // relu(hidden chunk) tile, same layout
     uint8_t* ring = sA2 + FFN_A_BYTES;              // FFN_STAGES x FFN_RING_BYTES
-    __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full[2], a2_empty[2],
+    __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full[2], a2_empty[2], a2_free,
         o_full[2], o_empty[2], y_full, h_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ volatile uint32_t s_prog;  // tiles the producer lane has started (paces the L2 prefetch of the residual rows)
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         s_prog = 0;
         for (int s = 0; s < FFN_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&a1_full, 1); mbar_init(&a1_empty, 1);
-        mbar_init(&y_full, 1); mbar_init(&h_full, G_EPI);
+        mbar_init(&y_full, 1); mbar_init(&h_full, G_EPI); mbar_init(&a2_free, 1);
         for (int a = 0; a < 2; a++) {
             mbar_init(&f_full[a], 1); mbar_init(&f_empty[a], G_EPI);
             mbar_init(&a2_full[a], G_EPI); mbar_init(&a2_empty[a], 1);  // per k-block of A2
@@ -678,39 +678,61 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             }
             if (FUSE_O) {
                 // ---- E0: X' = accO + bo + X (parked in TMEM), H = LN2(X') -> split bf16 -> over the O tile (A operand of FFN1)
-                float4 pre[2][4];
                 float* stg = s_stage[warp];
                 const float* xblk = g.X + ((size_t)tile * BM + wq * 32) * BN + ch;
-                warp_ldg_f32x16(lane, xblk, BN, pre[0]);       // requested before the wait for the MMAs, two blocks ahead
-                warp_ldg_f32x16(lane, xblk + 16, BN, pre[1]);
-                if (tid == 0) TR(1, 0);
-                mbar_wait(&y_full, n_done & 1);
-                if (tid == 0) TR(1, 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + 2 * BN + ch + ((uint32_t)(wq * 32) << 16);
                 const uint32_t txs = tmem_base + 3 * BN + ch + ((uint32_t)(wq * 32) << 16);
                 float x[64];
+                if (g.x_blocked) {
+                    // tile-blocked residual stream (see FfnArgs::x_blocked): the row owner's 16 loads are coalesced as they are, all
+                    // of them in flight before the wait for the MMAs
+                    const float* xt = g.X + (size_t)tile * BM * BN + (size_t)(ch >> 2) * (BM * 4) + r * 4;
+                    if (tid == 0) TR(1, 50);
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tacc + (uint32_t)c0, v);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        float rv[16];
-                        warp_xpose_f32x16(stg, lane, pre[h], rv);
-                        if (c0 + h * 16 + 32 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 32, BN, pre[h]);
-#pragma unroll
-                        for (int jj = 0; jj < 16; jj++) {
-                            x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_bo[ch + c0 + h * 16 + jj] + rv[jj];
-                            v[h * 16 + jj] = __float_as_uint(x[c0 + h * 16 + jj]);
-                        }
+                    for (int q = 0; q < 16; q++) {
+                        const float4 t = *(const float4*)(xt + q * (BM * 4));
+                        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
                     }
-                    tmem_st32(txs + (uint32_t)c0, v);
+                    if (tid == 0) TR(1, 0);
+                    mbar_wait(&y_full, n_done & 1);
+                    if (tid == 0) TR(1, 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tacc + (uint32_t)c0, v);
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++) {
+                            x[c0 + jj] += __uint_as_float(v[jj]) + s_bo[ch + c0 + jj];
+                            v[jj] = __float_as_uint(x[c0 + jj]);
+                        }
+                        tmem_st32(txs + (uint32_t)c0, v);
+                    }
+                } else {
+                    float4 pre[2][4];
+                    warp_ldg_f32x16(lane, xblk, BN, pre[0]);       // requested before the wait for the MMAs, two blocks ahead
+                    warp_ldg_f32x16(lane, xblk + 16, BN, pre[1]);
+                    mbar_wait(&y_full, n_done & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tacc + (uint32_t)c0, v);
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            float rv[16];
+                            warp_xpose_f32x16(stg, lane, pre[h], rv);
+                            if (c0 + h * 16 + 32 < 64) warp_ldg_f32x16(lane, xblk + c0 + h * 16 + 32, BN, pre[h]);
+#pragma unroll
+                            for (int jj = 0; jj < 16; jj++) {
+                                x[c0 + h * 16 + jj] = __uint_as_float(v[h * 16 + jj]) + s_bo[ch + c0 + h * 16 + jj] + rv[jj];
+                                v[h * 16 + jj] = __float_as_uint(x[c0 + h * 16 + jj]);
+                            }
+                        }
+                        tmem_st32(txs + (uint32_t)c0, v);
+                    }
                 }
-                if (tid == 0) {
-                    TR(1, 44);
-                    tma_store_wait_read();  // the previous tile's H tile has left A2 (the LayerNorm barriers below order E1(0)'s writes behind this)
-                }
+                if (tid == 0) TR(1, 44);
                 float sum = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < 64; jj++) sum += x[jj];
@@ -755,6 +777,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 0) TR(1, 4 + 4 * c);
                 const uint32_t taddr = tmem_base + j * BN + eh * 32 + ((uint32_t)(wq * 32) << 16);
+                if (FUSE_O && c == 0) {
+                    // the previous tile's H tile (staged in A2 by its final epilogue) has been read by its TMA store: long done by
+                    // now, so the thread that owns the bulk group confirms it here and not on E0's critical path
+                    if (tid == 0) { tma_store_wait_read(); mbar_arrive(&a2_free); }
+                    mbar_wait(&a2_free, n_done & 1);
+                }
 #pragma unroll
                 for (int kb = 0; kb < 2; kb++) {
                     mbar_wait(&a2_empty[kb], (na2 & 1) ^ 1);      // F2(c-1) has finished reading this k-block of A2
@@ -822,9 +850,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             mbar_arrive(&o_empty[oacc]);
             if (tid == 0) TR(1, 42);
             if (FUSE_O && g.store_x) {  // the residual stream is dead after the last layer: only its LayerNorm is consumed
+                if (g.x_blocked) {
+                    float* xt = g.X + (size_t)tile * BM * BN + (size_t)(ch >> 2) * (BM * 4) + r * 4;
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 16) warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                    for (int q = 0; q < 8; q++) *(float4*)(xt + q * (BM * 4)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    // (chunks 8..15 go out between the LayerNorm steps below: the store path is the bottleneck here, ~190 cycles per
+                    //  warp-wide 512-byte store, and stalls the issuing warp unless there is arithmetic to overlap it with)
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                }
             }
+            if (tid == 0) TR(1, 46);
             float sum = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) sum += x[jj];
@@ -841,6 +878,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             // LayerNorm(X) -> split bf16 -> the (idle) A2 tile in the layout of an operand tile ([kb][hi|lo][128 x 128 B], swizzled) ->
             // 4 TMA stores by one thread.  (Row-owner -> coalesced transposes through the per-warp staging buffers, 16 STS/LDS/STG
             // round trips per thread, were 5.8 k cycles of every tile during which nothing else could use the epilogue warps.)
+            if (tid == 0) TR(1, 47);
             uint8_t* orow = sA2 + (uint32_t)eh * (2 * BM * 128) + r * 128u;
 #pragma unroll
             for (int q8 = 0; q8 < 8; q8++) {
@@ -855,9 +893,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
                 const uint32_t off = (uint32_t)((q8 ^ (r & 7)) << 4);
                 *(uint4*)(orow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *(uint4*)(orow + BM * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if (FUSE_O && g.store_x && g.x_blocked) {
+                    float* xt = g.X + (size_t)tile * BM * BN + (size_t)(ch >> 2) * (BM * 4) + r * 4;
+                    const int q = 8 + q8;
+                    *(float4*)(xt + q * (BM * 4)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                }
             }
+            if (tid == 0) TR(1, 48);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (tid == 0) TR(1, 49);
             if (tid == 0) {
                 const int m0 = (int)(tile * BM);
                 for (int kb = 0; kb < 2; kb++) {
@@ -953,6 +998,12 @@ __device__ __forceinline__ void qa_store_row(uint8_t* hi_arr, uint8_t* lo_arr, i
     }
 }
 
+#ifdef HB_FFN_TRACE
+__device__ unsigned long long hb_qa_trace[3][2][64];  // [role: 0 MMA, 1 compute thread 0, 2 compute warp 4 lane 0][tile 10/11][event]
+#define TQ(role, k) do { if (blockIdx.x == 0 && (n_done == 10 || n_done == 11)) hb_qa_trace[role][n_done - 10][k] = clock64(); } while (0)
+#else
+#define TQ(role, k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, const __grid_constant__ CUtensorMap tmHhi,
                                                              const __grid_constant__ CUtensorMap tmHlo, const __grid_constant__ CUtensorMap tmWhi,
                                                              const __grid_constant__ CUtensorMap tmWlo) {
@@ -1010,9 +1061,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
             uint32_t it_stage = 0, n_done = 0;
             const uint32_t ab = smem_u32(sA);
             for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
+                TQ(0, 0);
                 mbar_wait_sleep(&a_full, n_done & 1);
+                TQ(0, 1);
                 for (int h = 0; h < 4; h++) {
+                    TQ(0, 2 + 4 * h);
                     mbar_wait_sleep(&h_empty[h], (n_done & 1) ^ 1);  // the previous tile's head h has been read out of this accumulator
+                    TQ(0, 3 + 4 * h);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + h * BN;
                     for (int kb = 0; kb < 2; kb++, it_stage++) {
@@ -1032,6 +1087,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                         umma_commit(&empty_bar[s]);
                     }
                     umma_commit(&h_full[h]);
+                    TQ(0, 4 + 4 * h);
                 }
                 umma_commit(&a_empty);  // H tile no longer needed
             }
@@ -1048,8 +1104,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
         for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
             for (int hh = 0; hh < 2; hh++) {
                 const int h = hh * 2 + wg;
+                const int trole = 1 + wg;
+                if (lane == 0 && wq == 0) TQ(trole, 0 + 10 * hh);
                 mbar_wait(&h_full[h], n_done & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0 && wq == 0) TQ(trole, 1 + 10 * hh);
                 const uint32_t taddr = tmem_base + h * BN + ((uint32_t)(wq * 32) << 16);
                 const float* bb = s_bias + h * QA_HROWS;
                 {
@@ -1060,6 +1119,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                     qa_store_row(aKh, aKl, lane, v, bb + 32, 1.f);
                 }
                 __syncwarp();
+                if (lane == 0 && wq == 0) TQ(trole, 2 + 10 * hh);
                 // ---- S = q·k^T: [32 queries][32 keys] as 2 x 4 accumulator tiles of m16n8
                 float sacc[2][4][4];
 #pragma unroll
@@ -1096,6 +1156,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                                 }
                         }
                 }
+                if (lane == 0 && wq == 0) TQ(trole, 3 + 10 * hh);
                 // ---- softmax over the 31 real keys (key 31 is the pad token).  A lane holds, for each of its 4 query rows
                 //      (gq + 8*i), the 8 keys {8*nt + 2*tq, +1}; the other 24 keys of a row are in the 3 neighbouring lanes.
                 float inv[2][2];
@@ -1121,6 +1182,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                         const int row = mt * 16 + hf * 8 + gq;
                         inv[mt][hf] = (row < R_COLS) ? 1.f / l : 0.f;  // the pad token's output row is written as zeros
                     }
+                if (lane == 0 && wq == 0) TQ(trole, 4 + 10 * hh);
                 // ---- v: read it out of TMEM only now (the Q arrays are free once every lane has its fragments)
                 __syncwarp();
                 {
@@ -1132,6 +1194,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&h_empty[h]);
                 __syncwarp();
+                if (lane == 0 && wq == 0) TQ(trole, 5 + 10 * hh);
                 // ---- O = P·v: P fragments come straight from the S accumulator layout (two n-tiles = one k16 A fragment)
                 float oacc[2][4][4];
 #pragma unroll
@@ -1166,6 +1229,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                             }
                     }
                 }
+                if (lane == 0 && wq == 0) TQ(trole, 6 + 10 * hh);
                 // ---- normalise, split, stage the 32 output rows (64 B of hi and of lo each) in the K arrays, store coalesced
                 uint32_t* sth = (uint32_t*)aKh;
                 uint32_t* stl = (uint32_t*)aKl;
@@ -1193,6 +1257,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_qkv_attn_ws(QkvAttnArgs g, con
                     *(uint4*)(g.out_lo + rb + (size_t)rr * BN + cq * 8) = *(const uint4*)(stl + w);
                 }
                 __syncwarp();
+                if (lane == 0 && wq == 0) TQ(trole, 7 + 10 * hh);
             }
         }
     }
@@ -1417,8 +1482,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[c0 + j] = 0.f;
                 }
-                warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
-                warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
+                if (g.x_blocked) {  // tile-blocked residual stream: the row owner's 16-byte stores are coalesced as they are
+                    float* xt = g.X + (size_t)item * BM * BN + (size_t)((ch + c0) >> 2) * (BM * 4) + r * 4;
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        *(float4*)(xt + q * (BM * 4)) = make_float4(x[c0 + 4 * q], x[c0 + 4 * q + 1], x[c0 + 4 * q + 2], x[c0 + 4 * q + 3]);
+                } else {
+                    warp_store_f32x16(stg, lane, xblk + c0, BN, x + c0);
+                    warp_store_f32x16(stg, lane, xblk + c0 + 16, BN, x + c0 + 16);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
@@ -1598,6 +1670,21 @@ cudaError_t qkv_attn_tc(const QkvAttnArgs& a, int num_sms, cudaStream_t st) {
         !make_tmap(&tWl, a.Wlo, 4 * QA_HROWS, BN, BN, QA_HROWS))
         return cudaErrorInvalidValue;
     k_qkv_attn_ws<<<(unsigned)std::min<uint32_t>(a.m_tiles, (uint32_t)num_sms), G_THREADS, smem, st>>>(a, tHh, tHl, tWh, tWl);
+#ifdef HB_FFN_TRACE
+    static int calls = 0;
+    if (++calls == 25 && a.m_tiles > 148 * 12) {
+        cudaStreamSynchronize(st);
+        static unsigned long long h[3][2][64];
+        cudaMemcpyFromSymbol(h, hb_qa_trace, sizeof(h));
+        const unsigned long long t0 = h[0][0][0];
+        for (int r = 0; r < 3; r++)
+            for (int t = 0; t < 2; t++) {
+                fprintf(stderr, "QATRACE role %d tile %d:", r, t);
+                for (int k = 0; k < 24; k++) fprintf(stderr, " %lld", h[r][t][k] ? (long long)(h[r][t][k] - t0) : -1LL);
+                fprintf(stderr, "\n");
+            }
+    }
+#endif
     return cudaGetLastError();
 }
 
