@@ -296,6 +296,7 @@ struct hb_ctx {
     std::string worker_err;
     bool idle() const { return queue.empty() && busy == 0; }
     size_t cap_hint[5] = {0, 0, 0, 0, 0};  // largest batch array sizes seen (tgt, win, ovl, ow, cig)
+    std::atomic<uint32_t> handed_total{0};  // batches handed over by all threads since the last flush (slow-start ramp)
     std::atomic<uint32_t> n_slots{0};       // submitting threads registered since the last flush
     std::atomic<bool> time_kernels{false};  // hb_set_kernel_timing
     uint64_t alloc_base[3] = {0, 0, 0};     // g_allocs / g_alloc_ns / g_submit_wait_ns at the last hb_reset_stats
@@ -895,7 +896,7 @@ int run_batch(hb_ctx* ctx, hb_ctx::Lane* L, HostBatch& hbt) {
 // Hand a staged batch to the launch worker (lock held); `b` is left empty (no capacity).
 // Back-pressure: at most 2 batches wait in the queue.
 void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b, uint32_t full_targets = 0) {
-    // full_targets != 0: this batch was cut short by the slow start; a steady-state hand-over will hold that many targets
+    // full_targets != 0: several threads submit, and a steady-state hand-over of one of them holds up to that many targets
     if (b.tgt.empty()) return;
     // capacity hint for staging batches: the largest arrays handed over so far plus a margin, so that pinned memory is
     // allocated once per batch object and then recycled.  (No extrapolation from partial batches: a two-target
@@ -905,10 +906,12 @@ void enqueue_batch(hb_ctx* ctx, std::unique_lock<std::mutex>& lk, HostBatch& b, 
     {
         size_t* h = ctx->cap_hint;
         const size_t cur[5] = {b.tgt.size(), b.win.size(), b.ovl.size(), b.ow.size(), b.cig.size()};
-        // Slow start makes the first batches smaller than a steady-state one: scale such a batch (at least 32 targets, a fair sample
-        // of the per-target sizes) up to the full hand-over size, so that the pool is pinned once at its final size.  Only batches
-        // that the slow start cut are scaled (never a flush remainder, never against an "everything in one launch" launch_targets),
-        // and by at most 16x.
+        // Slow start and flush remainders are smaller than a steady-state batch: scale such a batch (at least 32 targets, a fair
+        // sample of the per-target sizes) up to the full hand-over size (at most 1 024 targets, at most 16x), so that the pool is
+        // pinned once, at its final size, during warm-up.  (A rank of a strong-scaling job only ever hands over remainders whose
+        // size depends on how its threads happened to share a step; the largest one seen so far + 25 % was exceeded inside the
+        // timed region on 2 of 8 ranks: every pooled batch re-pinned, 51 cudaHostAlloc calls, 1 s.)  Never with a single
+        // submitting thread: tests hand over everything in one launch.
         const double scale = (full_targets && cur[0] >= 32 && cur[0] < full_targets) ? std::min(16.0, (double)full_targets / (double)cur[0]) : 1.0;
         for (int i = 0; i < 5; i++) {
             const size_t want = (size_t)((double)cur[i] * scale);
@@ -1190,15 +1193,22 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
     // ... but never less than 256 targets per launch (unless launch_targets itself is smaller): ~1 300 windows is what it takes to
     // fill 148 SMs with the one-CTA-per-window feature kernels and to amortise the ~25 launches of a batch
     uint32_t thr = std::min(lt, std::max(256u, lt / ns));
-    // slow start: with several submitting threads, the first batches of each are small (64, 128, 256, ... targets) so that the GPU
-    // has work a few milliseconds after the first submit instead of after a whole launch has been staged (a single submitting
-    // thread keeps exact launch sizes: tests and the isolated launch bench.py times rely on them)
+    // slow start: with several submitting threads, the first hand-overs after a flush are small and grow geometrically (48, 72, 108, ...
+    // targets, counted over all threads), so that the GPU has work a few milliseconds after the first submit instead of after a
+    // whole launch has been staged, and the threads - which fill their batches at the same rate - do not all hand over at the
+    // same moment.  (A single submitting thread keeps exact launch sizes: tests and the isolated launch bench.py times rely on
+    // them.)  Matters when a run is short: a rank of an 8-GPU strong-scaling job sees ~100 ms of work.
     const uint32_t full_thr = thr;
-    if (ns >= 2 && slot->handed < 4) thr = std::min(thr, 64u << slot->handed);
+    if (ns >= 2) {
+        static const uint16_t ramp[5] = {48, 72, 108, 162, 243};
+        const uint32_t n = ctx->handed_total.load(std::memory_order_relaxed);
+        if (n < 5) thr = std::min<uint32_t>(thr, ramp[n]);
+    }
     if (slot->batch.tgt.size() >= thr) {
         std::unique_lock<std::mutex> lk(ctx->mu);
-        enqueue_batch(ctx, lk, slot->batch, thr < full_thr ? full_thr : 0u);
+        enqueue_batch(ctx, lk, slot->batch, ns >= 2 ? std::min(full_thr, 1024u) : 0u);
         slot->handed++;
+        ctx->handed_total.fetch_add(1, std::memory_order_relaxed);
     }
     return HB_OK;
 }
@@ -1464,7 +1474,12 @@ int hb_set_kernel_timing(hb_ctx* ctx, int on) {
 int hb_flush(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->mu);
-    for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch);  // must not race with hb_submit_* (see header)
+    {
+        const uint32_t lt = ctx->opt.launch_targets, ns = std::max<uint32_t>(1u, (uint32_t)ctx->slots.size());
+        const uint32_t full = ns >= 2 ? std::min(std::min(lt, std::max(256u, lt / ns)), 1024u) : 0u;
+        for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch, full);  // must not race with hb_submit_* (see header)
+    }
+    ctx->handed_total.store(0);
     ctx->slots.clear();                                  // slots of finished feature threads are dropped;
     ctx->n_slots.store(0);
     ctx->generation = g_ctx_generation.fetch_add(1);    // live threads re-register on their next submit

@@ -1284,6 +1284,12 @@ constexpr int STEM_RP_LD = 132;                         // row stride (floats) o
 // 13-14 gather (token/quality neighbourhoods from the pileup matrix, one item ahead)
 constexpr int S_EPI = 256, S_PROD = 128, S_GATHER = 64, S_THREADS = 480, S_MMA_WARP = 12;
 
+#ifdef HB_FFN_TRACE
+__device__ unsigned long long hb_st_trace[4][2][32];  // [role: 0 MMA, 1 epilogue thread 0, 2 producer thread 0, 3 gather thread 0][item 10/11][event]
+#define TS_(role, k) do { if (blockIdx.x == 0 && (n_done == 10 || n_done == 11)) hb_st_trace[role][n_done - 10][k] = clock64(); } while (0)
+#else
+#define TS_(role, k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs g, const __grid_constant__ CUtensorMap tmWhi,
                                                          const __grid_constant__ CUtensorMap tmWlo) {
     extern __shared__ uint8_t smem_dyn[];
@@ -1335,12 +1341,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint8_t* tb = tokbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
             const uint8_t* qb = qbuf + (n_done & 1) * 4 * STEM_MAXK * 32;
+            if (p == 0) TS_(2, 0);
             mbar_wait(&buf_full[n_done & 1], (n_done >> 1) & 1);  // the gather warps have staged this item's neighbourhood
+            if (p == 0) TS_(2, 1);
             const uint8_t* trow = tb + pos * STEM_MAXK * 32 + rd;  // this row's token of tap j at trow[j * 32]
             const uint8_t* qrow = qb + pos * STEM_MAXK * 32 + rd;
             for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
                 const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                if (p == 0 && kb < 9) TS_(2, 2 + 2 * kb);
                 uint8_t* sA = smem + (size_t)s * STEM_STAGE_BYTES;
                 if (p == 0) {  // W' k-block (hi, lo) by TMA
                     mbar_arrive_expect_tx(&full_bar[s], 2 * BN * 128);
@@ -1381,6 +1390,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&full_bar[s]);
+                if (p == 0 && kb < 9) TS_(2, 3 + 2 * kb);
             }
             mbar_arrive(&buf_empty[n_done & 1]);  // the staging buffer may be refilled
         }
@@ -1400,7 +1410,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 m_row = b.fwd_row[g.n0 + item * 4 + lane];
                 m_L = b.w_L[w]; m_Lref = b.w_reflmax[w]; m_base = b.w_rowbase[w];
             }
+            if (gt == 0) TS_(3, 0);
             mbar_wait(&buf_empty[n_done & 1], ((n_done >> 1) & 1) ^ 1);
+            if (gt == 0) TS_(3, 1);
             for (int i0 = 0; i0 < 4 * K * 2; i0 += S_GATHER) {  // one 16-byte half row per iteration (warp-uniform trip count)
                 const int i = i0 + gt;
                 const int ps = min(i / (K * 2), 3), rem = i % (K * 2), j = rem >> 1, half = rem & 1;
@@ -1424,6 +1436,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 }
             }
             mbar_arrive(&buf_full[n_done & 1]);
+            if (gt == 0) TS_(3, 2);
         }
     } else if (warp == S_MMA_WARP) {
         // =============================== MMA issuer ===============================
@@ -1431,12 +1444,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
             uint32_t it_stage = 0, n_done = 0;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
                 const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+                TS_(0, 0);
                 mbar_wait(&tempty_bar[acc], aph ^ 1);
+                TS_(0, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (uint32_t kb = 0; kb < kbs; kb++, it_stage++) {
                     const uint32_t s = it_stage % STAGES, ph = (it_stage / STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
+                    if (kb < 9) TS_(0, 2 + kb);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sb = smem_u32(smem + (size_t)s * STEM_STAGE_BYTES);
                     const uint64_t dA = make_desc(sb);
@@ -1450,6 +1466,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&tfull_bar[acc]);
+                TS_(0, 12);
             }
         }
     } else if (warp < 8) {
@@ -1460,7 +1477,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
         uint32_t n_done = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
             const uint32_t acc = n_done & 1, aph = (n_done >> 1) & 1;
+            if (tid == 0) TS_(1, 0);
             mbar_wait(&tfull_bar[acc], aph);
+            if (tid == 0) TS_(1, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // token row: position = item*4 + wq, read = lane
             const uint32_t r = wq * 32 + lane;
@@ -1494,6 +1513,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
+            if (tid == 0) TS_(1, 2);
             if (g.out_hi) {
                 // LayerNorm of the row (layer 0's ln1) -> split bf16: the operand of the first QKV projection.
                 // Partial sums are exchanged with the thread that owns the other 64 columns of the row.
@@ -1510,6 +1530,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                 s_red[acc][eh][r] = var;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 const float rstd = rsqrtf((s_red[acc][0][r] + s_red[acc][1][r]) * (1.f / BN) + 1e-5f);
+                if (tid == 0) TS_(1, 3);
                 __nv_bfloat16* hblk = g.out_hi + ((size_t)item * BM + wq * 32) * BN + ch;
                 __nv_bfloat16* lblk = g.out_lo + ((size_t)item * BM + wq * 32) * BN + ch;
 #pragma unroll
@@ -1522,6 +1543,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_stem_tc(BatchView b, StemArgs 
                     warp_store_bf16x16((uint32_t*)stg, lane, hblk + j, BN, hi);
                     warp_store_bf16x16((uint32_t*)stg, lane, lblk + j, BN, lo);
                 }
+                if (tid == 0) TS_(1, 4);
             }
         }
     }
@@ -1652,6 +1674,21 @@ cudaError_t stem_tc(const BatchView& b, const StemArgs& a, int num_sms, cudaStre
     CUtensorMap tWh, tWl;
     if (!make_tmap(&tWh, a.Whi, BN, a.Kp, a.Kp) || !make_tmap(&tWl, a.Wlo, BN, a.Kp, a.Kp)) return cudaErrorInvalidValue;
     k_stem_tc<<<(unsigned)std::min<uint32_t>(items, (uint32_t)num_sms), S_THREADS, smem, st>>>(b, a, tWh, tWl);
+#ifdef HB_FFN_TRACE
+    static int calls = 0;
+    if (++calls == 13 && items > 148 * 12) {
+        cudaStreamSynchronize(st);
+        static unsigned long long h[4][2][32];
+        cudaMemcpyFromSymbol(h, hb_st_trace, sizeof(h));
+        const unsigned long long t0 = h[0][0][0];
+        for (int r = 0; r < 4; r++)
+            for (int t = 0; t < 2; t++) {
+                fprintf(stderr, "STTRACE role %d item %d:", r, t);
+                for (int k = 0; k < 22; k++) fprintf(stderr, " %lld", h[r][t][k] ? (long long)(h[r][t][k] - t0) : -1LL);
+                fprintf(stderr, "\n");
+            }
+    }
+#endif
     return cudaGetLastError();
 }
 
