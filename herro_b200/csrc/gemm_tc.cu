@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
     __shared__ uint64_t full_bar[FFN_STAGES], empty_bar[FFN_STAGES], a1_full, a1_empty, f_full[2], f_empty[2], a2_full[2], a2_empty[2], a2_free,
         o_full[2], o_empty[2], y_full, h_full;
     __shared__ uint32_t tmem_base_s;
-    __shared__ volatile uint32_t s_prog;  // tiles the producer lane has started (paces the L2 prefetch of the residual rows)
+    __shared__ uint32_t s_prog;  // tiles the producer lane has started (paces the L2 prefetch of the residual rows)
     __shared__ __align__(16) float s_b1[512], s_b2[BN], s_lng[BN], s_lnb[BN], s_bo[BN], s_ln2g[BN], s_ln2b[BN];
     __shared__ float s_red[2][2][BM], s_red2[2][2][BM];  // [slot][column half][row]: LayerNorm partial sums / squared deviations
     __shared__ __align__(16) float s_stage[8][32 * 16];  // per-warp transpose buffers (see warp_store_f32x16)
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
         if (FUSE_O && lane != 0) {
             uint32_t n = 0;
             for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n++) {
-                while ((int)(n - s_prog) > 1) __nanosleep(1000);  // at most one tile ahead of the tile lane 0 is loading
+                while ((int)(n - atomicAdd(&s_prog, 0u)) > 1) __nanosleep(1000);  // at most one tile ahead of the tile lane 0 is loading
                 for (int i = lane - 1; i < BM * 4; i += 31) prefetch_l2((const char*)(g.X + (size_t)tile * BM * BN) + (size_t)i * 128);
             }
         }
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_ffn_ws(FfnArgs g, const __grid
             };
             if (blockIdx.x < g.m_tiles) load_a1(blockIdx.x, 0);
             for (uint32_t tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, n_done++) {
-                s_prog = n_done;
+                atomicExch(&s_prog, n_done);  // (atomics: a progress flag polled by the other lanes, not a data hand-off)
                 if (FUSE_O) {  // Wo: 2 k-block tiles, ahead of the FFN weights
                     for (int kb = 0; kb < 2; kb++, it_stage++) {
                         const uint32_t s = it_stage % FFN_STAGES, ph = (it_stage / FFN_STAGES) & 1;
