@@ -98,13 +98,14 @@ def load_library():
     L.hb_debug_dump_window.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp]
     L.hb_replay_last_launch.argtypes = [vp, u32, C.POINTER(C.c_float)]
     L.hb_dump_features.argtypes = [vp, u32, C.c_char_p, vp]
+    L.hb_inspect_model.argtypes = [C.c_char_p, u32p, C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
     fp = C.POINTER(C.c_float)
     L.hb_selftest_gemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, C.c_int, u32, fp, fp, fp, fp]
     _lib = L
     return L
 
 
-EXPORTED_SYMBOLS = ["hb_dump_features", "hb_window_range", "hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
+EXPORTED_SYMBOLS = ["hb_inspect_model", "hb_dump_features", "hb_window_range", "hb_bind_calling_thread", "hb_set_launch_targets", "hb_set_kernel_timing", "hb_extract_windows", "hb_create", "hb_destroy", "hb_upload_reads", "hb_submit_target", "hb_submit_alignments", "hb_flush",
                     "hb_poll_corrected", "hb_release_result", "hb_last_error", "hb_get_stats", "hb_reset_stats",
                     "hb_debug_window_shape", "hb_debug_dump_window", "hb_replay_last_launch", "hb_selftest_gemm"]
 
@@ -153,6 +154,18 @@ def extract_windows(overlaps: np.ndarray, window_size: int, n_windows: int) -> n
     if rc != 0:
         raise HerroError(rc, "alignment on which the reference would panic")
     return out[:n.value]
+
+
+def inspect_model(path: str):
+    """Architecture and parameter hash of a model file (HB200W1 blob or TorchScript archive), host only (hb_inspect_model)."""
+    L = load_library()
+    dims = (C.c_uint32 * 6)()
+    h = C.c_uint64()
+    err = C.create_string_buffer(512)
+    rc = L.hb_inspect_model(path.encode(), dims, C.byref(h), err, len(err))
+    if rc != 0:
+        raise HerroError(rc, err.value.decode(errors="replace"))
+    return dict(zip(("stem_k", "channels", "heads", "layers", "ffn", "collapse"), [int(x) for x in dims])), int(h.value)
 
 
 def window_range(overlap: np.ndarray, window_size: int, n_windows: int):

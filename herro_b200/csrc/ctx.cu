@@ -14,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -29,6 +30,7 @@
 #include "common.cuh"
 #include "forward.h"
 #include "windowing.h"
+#include "torchscript.h"
 
 using namespace hb;
 
@@ -386,42 +388,76 @@ void probe_numa(hb_ctx* ctx) {
     ctx->numa_node = node;
 }
 
-int load_weights(hb_ctx* ctx, const char* path) {
+// A model file as the canonical tensor table (names and forms of herro_b200/weights.py): either the HB200W1 blob, or a
+// TorchScript archive of the same architecture - what the reference's `-m` names (src/inference.rs:185) - read by torchscript.cpp.
+struct ModelFile {
+    uint32_t cfg[10] = {0};  // tokens, emb, reads, stem_k, C, H, layers, F, D, classes
+    std::map<std::string, std::vector<float>> T;
+};
+int read_model_file(const char* path, ModelFile& mf, std::string& err) {
     FILE* f = fopen(path, "rb");
-    if (!f) return fail(ctx, HB_ERR_MODEL, std::string("cannot open model file ") + path);
+    if (!f) { err = std::string("cannot open model file ") + path; return HB_ERR_MODEL; }
     fseek(f, 0, SEEK_END);
     long sz = ftell(f);
     fseek(f, 0, SEEK_SET);
-    if (sz < 0) { fclose(f); return fail(ctx, HB_ERR_MODEL, "cannot size model file"); }
+    if (sz < 0) { fclose(f); err = "cannot size model file"; return HB_ERR_MODEL; }
     std::vector<uint8_t> buf((size_t)sz);
-    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(ctx, HB_ERR_MODEL, "short read on model file"); }
+    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); err = "short read on model file"; return HB_ERR_MODEL; }
     fclose(f);
-    if ((size_t)sz < sizeof(BlobHeader)) return fail(ctx, HB_ERR_MODEL, "model file too small");
+    if (ts_is_zip(buf.data(), buf.size())) {
+        TsModel m;
+        if (!ts_read_archive(buf.data(), buf.size(), m)) { err = "TorchScript archive: " + m.err; return HB_ERR_MODEL; }
+        TsDims d;
+        if (!ts_to_canonical(m, 4, d, mf.T, err)) { err = "TorchScript archive: " + err; return HB_ERR_MODEL; }
+        const uint32_t c[10] = {12, 6, 31, (uint32_t)d.stem_k, (uint32_t)d.channels, (uint32_t)d.heads, (uint32_t)d.layers, (uint32_t)d.ffn, (uint32_t)d.collapse, 5};
+        memcpy(mf.cfg, c, sizeof c);
+        return HB_OK;
+    }
+    if ((size_t)sz < sizeof(BlobHeader)) { err = "model file too small"; return HB_ERR_MODEL; }
     BlobHeader h;
     memcpy(&h, buf.data(), sizeof h);
-    if (memcmp(h.magic, "HB200W1\0", 8) != 0 || h.version != 1)
-        return fail(ctx, HB_ERR_MODEL, "not an HB200W1 weights blob (convert TorchScript archives with tools/export_weights.py)");
-    if (h.cfg[0] != 12 || h.cfg[1] != 6 || h.cfg[2] != 31 || h.cfg[9] != 5)
+    if (memcmp(h.magic, "HB200W1\0", 8) != 0 || h.version != 1) {
+        err = "neither an HB200W1 weights blob nor a TorchScript archive";
+        return HB_ERR_MODEL;
+    }
+    memcpy(mf.cfg, h.cfg, sizeof mf.cfg);
+    for (uint32_t i = 0; i < h.n_tensors; i++) {
+        BlobEntry e;
+        size_t eo = sizeof(BlobHeader) + (size_t)i * sizeof(BlobEntry);
+        if (eo + sizeof e > (size_t)sz) { err = "truncated tensor table"; return HB_ERR_MODEL; }
+        memcpy(&e, buf.data() + eo, sizeof e);
+        if (e.dtype != 0 || e.offset > (uint64_t)sz || e.nbytes > (uint64_t)sz - e.offset || (e.offset & 3u) || (e.nbytes & 3u)) {
+            err = "bad tensor entry";
+            return HB_ERR_MODEL;
+        }
+        char nm[49];
+        memcpy(nm, e.name, 48);
+        nm[48] = 0;
+        std::vector<float>& v = mf.T[nm];
+        v.resize((size_t)(e.nbytes / 4));
+        memcpy(v.data(), buf.data() + e.offset, (size_t)e.nbytes);
+    }
+    return HB_OK;
+}
+
+int load_weights(hb_ctx* ctx, const char* path) {
+    ModelFile mf;
+    {
+        std::string e;
+        const int rc = read_model_file(path, mf, e);
+        if (rc != HB_OK) return fail(ctx, rc, e);
+    }
+    const uint32_t* cfg = mf.cfg;
+    if (cfg[0] != 12 || cfg[1] != 6 || cfg[2] != 31 || cfg[9] != 5)
         return fail(ctx, HB_ERR_MODEL, "unsupported fixed dimensions (tokens/emb/reads/classes)");
     FwdWeights& wt = ctx->wt;
-    wt.stem_k = (int)h.cfg[3]; wt.C = (int)h.cfg[4]; wt.H = (int)h.cfg[5]; wt.layers = (int)h.cfg[6];
-    wt.F = (int)h.cfg[7]; wt.D = (int)h.cfg[8];
+    wt.stem_k = (int)cfg[3]; wt.C = (int)cfg[4]; wt.H = (int)cfg[5]; wt.layers = (int)cfg[6];
+    wt.F = (int)cfg[7]; wt.D = (int)cfg[8];
     if (wt.layers < 1 || wt.layers > MAX_LAYERS || wt.H < 1 || wt.C % wt.H || (wt.C / wt.H != 16 && wt.C / wt.H != 32) ||
         wt.C % 128 || wt.F % 128 || wt.D % 128 || !(wt.stem_k & 1) || wt.stem_k > 129 || wt.C > 1024)
         return fail(ctx, HB_ERR_MODEL, "unsupported model dimensions (need C,F,D % 128 == 0, head_dim 16 or 32, odd stem_k)");
     std::unordered_map<std::string, std::pair<const float*, size_t>> T;
-    for (uint32_t i = 0; i < h.n_tensors; i++) {
-        BlobEntry e;
-        size_t eo = sizeof(BlobHeader) + (size_t)i * sizeof(BlobEntry);
-        if (eo + sizeof e > (size_t)sz) return fail(ctx, HB_ERR_MODEL, "truncated tensor table");
-        memcpy(&e, buf.data() + eo, sizeof e);
-        if (e.dtype != 0 || e.offset > (uint64_t)sz || e.nbytes > (uint64_t)sz - e.offset || (e.offset & 3u))
-            return fail(ctx, HB_ERR_MODEL, "bad tensor entry");
-        char nm[49];
-        memcpy(nm, e.name, 48);
-        nm[48] = 0;
-        T[nm] = {(const float*)(buf.data() + e.offset), (size_t)(e.nbytes / 4)};
-    }
+    for (auto& kv : mf.T) T[kv.first] = {kv.second.data(), kv.second.size()};
     auto need = [&](const std::string& n, size_t count, const float*& hostp) -> bool {
         auto it = T.find(n);
         if (it == T.end() || it->second.second != count) { ctx->err = "missing/mis-sized tensor " + n; return false; }
@@ -1217,6 +1253,28 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
 
 // ========================================================================================
 extern "C" {
+
+int hb_inspect_model(const char* model_path, uint32_t dims[6], uint64_t* params_hash, char* err, size_t err_cap) {
+    if (!model_path || !dims) return HB_ERR_ARG;
+    ModelFile mf;
+    std::string e;
+    const int rc = read_model_file(model_path, mf, e);
+    if (rc != HB_OK) {
+        if (err && err_cap) { strncpy(err, e.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+        return rc;
+    }
+    for (int i = 0; i < 6; i++) dims[i] = mf.cfg[3 + i];
+    if (params_hash) {  // FNV-1a over the canonical tensors in name order: equal for a blob and an archive of the same weights
+        uint64_t h = 1469598103934665603ull;
+        for (auto& kv : mf.T) {
+            for (unsigned char c : kv.first) { h ^= c; h *= 1099511628211ull; }
+            const uint8_t* p = (const uint8_t*)kv.second.data();
+            for (size_t i = 0; i < kv.second.size() * 4; i++) { h ^= p[i]; h *= 1099511628211ull; }
+        }
+        *params_hash = h;
+    }
+    return HB_OK;
+}
 
 const char* hb_last_error(hb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 

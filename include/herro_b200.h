@@ -80,10 +80,18 @@ typedef struct hb_options {
 
 typedef struct hb_ctx hb_ctx; /* one per GPU: streams, weights, read-store replica, staging buffers */
 
-/* Create a context on `cuda_device` and load the forward weights (HB200W1 blob, see
- * herro_b200/weights.py; replaces tch::CModule::load_on_device, src/inference.rs:185). */
+/* Create a context on `cuda_device` and load the forward weights (replaces tch::CModule::load_on_device,
+ * src/inference.rs:185).  `model_path` is what `-m` names: a TorchScript archive (`torch.jit.save`; ZIP with stored
+ * entries + data.pkl, read natively, no libtorch) of a module with the architecture this library implements
+ * (oracle/forward_ref.py naming; an optional `stem_bn` is folded), or the HB200W1 blob of herro_b200/weights.py.
+ * Any other graph is HB_ERR_MODEL with the first missing parameter named: TorchScript code is not executed. */
 int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_options* opt);
 void hb_destroy(hb_ctx* ctx);
+
+/* Architecture of a model file without creating a context (host only, no CUDA call): dims = stem_k, channels, heads,
+ * layers, ffn, collapse; *params_hash (may be NULL) = FNV-1a-64 over the canonical fp32 tensors in name order, equal for
+ * a blob and an archive holding the same weights.  `err` (may be NULL) receives the message on failure. */
+int hb_inspect_model(const char* model_path, uint32_t dims[6], uint64_t* params_hash, char* err, size_t err_cap);
 
 /* Replicate the read store on the GPU.  Layout is HAECRecord verbatim (src/haec_io.rs:19-24,
  * 77-81): seq_words[i] = 2-bit little-endian packing, 32 bases per u64, A0 C1 G2 T3

@@ -189,3 +189,19 @@ def test_native_pipeline_multithreaded_equals_single_threaded(tmp_path):
         assert r["failed_targets"] == 0 and r["records"] > 0
         outs.append(sorted(open(out, "rb").read().split(b">")[1:]))
     assert outs[0] == outs[1]
+
+
+def test_torchscript_archive_as_model(tmp_path):
+    """`-m model.pt` (src/inference.rs:185): a TorchScript archive of the stand-in graph is read natively by hb_create
+    (torchscript.cpp) and corrects exactly like the HB200W1 blob holding the same weights."""
+    torch = pytest.importorskip("torch")
+    from oracle import forward_ref
+    from herro_b200 import weights as hbw
+    rs = helpers.small_readset(n_reads=20, mean_len=6000, seed=31)
+    blob = helpers.model_path(seed=3)
+    cfg, T = hbw.load_blob(blob)
+    pt = str(tmp_path / "model.pt")
+    torch.jit.script(forward_ref.from_weights(cfg, T)).save(pt)
+    a = helpers.run_product(rs, blob, 4096, 64)
+    b = helpers.run_product(rs, pt, 4096, 64)
+    assert a["segments"] == b["segments"] and any(a["segments"].values())
