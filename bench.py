@@ -57,8 +57,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--feature-threads", type=int, default=8, help="reference -t: host threads submitting targets (4 threads stage ~40 targets/ms, about what one B200 consumes)")
-    ap.add_argument("--e2e-launch-targets", type=int, default=4000, help="hb_options.launch_targets in the e2e regions (shared by the feature "
-                    "threads: each hands over launch_targets / threads targets per device launch)")
+    ap.add_argument("--e2e-launch-targets", type=int, default=2000, help="hb_options.launch_targets in the e2e regions (shared by the feature "
+                    "threads: each hands over max(256, launch_targets / threads) targets per device launch; measured on cfg3 with 8 threads: "
+                    "256-target launches 800-868 Mbases/s, 500: 785-796, 1000: 709, 2000: 584 - smaller launches overlap better across the lanes)")
     ap.add_argument("--host-windowing", action="store_true", help="e2e region submits host-computed OverlapWindows (hb_submit_target) instead of raw alignments")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU legs (cpu_baseline / --impl reference); 0 = all host threads")
     return ap.parse_args()

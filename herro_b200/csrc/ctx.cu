@@ -281,6 +281,7 @@ struct hb_ctx {
     static constexpr int MAX_LANES = 4;
     Lane lanes[MAX_LANES];
     int n_lanes = 3;     // HERRO_B200_LANES overrides (1..4)
+    uint32_t min_launch = 256;  // smallest per-thread hand-over unless launch_targets itself is smaller (HERRO_B200_MIN_LAUNCH: experiments)
     int last_lane = -1;  // lane of the most recently finished launch (debug taps / replay)
     uint32_t chunk_pos = 65536;  // supported positions per forward pass (HERRO_B200_CHUNK_POS): one pass per launch unless huge
 
@@ -1228,7 +1229,7 @@ int stage_target(hb_ctx* ctx, const PreparedTarget& P, const hb_overlap* ovl, ui
     const uint32_t lt = ctx->opt.launch_targets, ns = std::max(1u, ctx->n_slots.load(std::memory_order_relaxed));
     // ... but never less than 256 targets per launch (unless launch_targets itself is smaller): ~1 300 windows is what it takes to
     // fill 148 SMs with the one-CTA-per-window feature kernels and to amortise the ~25 launches of a batch
-    uint32_t thr = std::min(lt, std::max(256u, lt / ns));
+    uint32_t thr = std::min(lt, std::max(ctx->min_launch, lt / ns));
     // slow start: with several submitting threads, the first hand-overs after a flush are small and grow geometrically (48, 72, 108, ...
     // targets, counted over all threads), so that the GPU has work a few milliseconds after the first submit instead of after a
     // whole launch has been staged, and the threads - which fill their batches at the same rate - do not all hand over at the
@@ -1306,6 +1307,7 @@ int hb_create(hb_ctx** out, int cuda_device, const char* model_path, const hb_op
     if (cudaSetDevice(cuda_device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(HB_ERR_CUDA); }
     if (const char* e = getenv("HERRO_B200_CHUNK_POS")) ctx->chunk_pos = (uint32_t)std::min(std::max(atoi(e), 128), 65536);
     if (const char* e = getenv("HERRO_B200_LANES")) ctx->n_lanes = std::min(std::max(atoi(e), 1), (int)hb_ctx::MAX_LANES);
+    if (const char* e = getenv("HERRO_B200_MIN_LAUNCH")) ctx->min_launch = (uint32_t)std::min(std::max(atoi(e), 16), 4096);
     // debugging aids / A-B parity tests: read here once, never on the launch path
     ctx->pileup_v1 = getenv("HERRO_B200_PILEUP_V1") != nullptr;
     ctx->host_windowing = getenv("HERRO_B200_HOST_WINDOWING") != nullptr;
@@ -1534,7 +1536,7 @@ int hb_flush(hb_ctx* ctx) {
     std::unique_lock<std::mutex> lk(ctx->mu);
     {
         const uint32_t lt = ctx->opt.launch_targets, ns = std::max<uint32_t>(1u, (uint32_t)ctx->slots.size());
-        const uint32_t full = ns >= 2 ? std::min(std::min(lt, std::max(256u, lt / ns)), 1024u) : 0u;
+        const uint32_t full = ns >= 2 ? std::min(std::min(lt, std::max(ctx->min_launch, lt / ns)), 1024u) : 0u;
         for (auto& sl : ctx->slots) enqueue_batch(ctx, lk, sl->batch, full);  // must not race with hb_submit_* (see header)
     }
     ctx->handed_total.store(0);
