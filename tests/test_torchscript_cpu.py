@@ -115,3 +115,38 @@ def test_foreign_graphs_and_damaged_archives_are_rejected(tmp_path):
     with pytest.raises(HerroError) as ei:
         api.inspect_model(bad)
     assert "outside its storage" in str(ei.value)
+
+
+def test_mutated_archives_never_crash_the_reader(tmp_path):
+    """A model file is untrusted input: random byte flips in the pickle, the central directory or anywhere, and truncations, must end
+    in a result or HB_ERR_MODEL (the same corpus was run under ASan/UBSan against torchscript.cpp when it was written)."""
+    import random
+    from herro_b200.api import HerroError
+    cfg, net = _net(seed=3)
+    good = str(tmp_path / "good.pt")
+    torch.jit.script(net).save(good)
+    raw = open(good, "rb").read()
+    with zipfile.ZipFile(good) as z:
+        pk = [i for i in z.infolist() if i.filename.endswith("data.pkl")][0]
+        cd = z.start_dir
+    rnd = random.Random(11)
+    p = str(tmp_path / "m.pt")
+    outcomes = {"ok": 0, "rejected": 0}
+    for _ in range(250):
+        b = bytearray(raw)
+        region = rnd.choice(["pkl", "cd", "any", "trunc"])
+        if region == "trunc":
+            b = b[: rnd.randrange(len(b))]
+        else:
+            for _ in range(rnd.choice([1, 2, 4, 8])):
+                pos = {"pkl": rnd.randrange(pk.header_offset, pk.header_offset + pk.file_size + 200), "cd": rnd.randrange(cd, len(b)),
+                       "any": rnd.randrange(len(b))}[region]
+                b[pos] = rnd.randrange(256)
+        open(p, "wb").write(b)
+        try:
+            api.inspect_model(p)
+            outcomes["ok"] += 1
+        except HerroError as e:
+            assert e.code == HB_ERR_MODEL
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 50 and outcomes["ok"] > 20
