@@ -553,33 +553,35 @@ int hbh_inference(const char* reads_path, const char* alns_dir, const char* mode
     hbh_reads* R = nullptr;
     int rc = hbh_reads_load(reads_path, window, core, n_core, neighbour, n_neigh, io_threads, &R);
     if (rc) return rc;
-    const double t_al0 = now_s();
-    hbh_alns* A = nullptr;
-    rc = hbh_alns_load(alns_dir, R, core, n_core, io_threads, &A);
-    if (rc) { hbh_reads_free(R); return rc; }
-    const double t_ingest = now_s() - t_al0;
+    // Context creation (CUDA initialisation, weights) and the read-store upload of every device run while the alignment batches are
+    // decompressed and parsed on the host: the two need nothing from each other (both only read `R`).
     std::vector<hb_ctx*> ctx((size_t)n_dev, nullptr);
     hb_options opt{};
     opt.struct_size = sizeof opt; opt.window_size = window; opt.batch_size = batch;
     std::vector<double> t_up((size_t)n_dev, 0);
-    auto cleanup = [&]() { for (hb_ctx* c : ctx) if (c) hb_destroy(c); hbh_alns_free(A); hbh_reads_free(R); };
-    {
-        std::vector<std::thread> th;
-        std::atomic<int> bad{0};
-        for (int d = 0; d < n_dev; d++)
-            th.emplace_back([&, d]() {
-                if (hb_create(&ctx[d], devices[d], model, &opt) != HB_OK) { bad = HB_ERR_CUDA; return; }
-                const double t0 = now_s();
-                if (hb_upload_reads(ctx[d], hbh_reads_count(R), hbh_reads_word_ptrs(R), hbh_reads_lens(R), hbh_reads_qual_ptrs(R)) != HB_OK) bad = HB_ERR_CUDA;
-                t_up[d] = now_s() - t0;
-            });
-        for (auto& t : th) t.join();
-        if (bad.load()) {
-            t_err = "context creation / read-store upload failed";
-            for (hb_ctx* c : ctx) if (c) { t_err += std::string(": ") + hb_last_error(c); break; }
-            cleanup();
-            return bad.load();
-        }
+    hbh_alns* A = nullptr;
+    auto cleanup = [&]() { for (hb_ctx* c : ctx) if (c) hb_destroy(c); if (A) hbh_alns_free(A); hbh_reads_free(R); };
+    std::atomic<int> bad{0};
+    std::vector<std::thread> dev_th;
+    for (int d = 0; d < n_dev; d++)
+        dev_th.emplace_back([&, d]() {
+            if (hb_create(&ctx[d], devices[d], model, &opt) != HB_OK) { bad = HB_ERR_CUDA; return; }
+            const double t0 = now_s();
+            if (hb_upload_reads(ctx[d], hbh_reads_count(R), hbh_reads_word_ptrs(R), hbh_reads_lens(R), hbh_reads_qual_ptrs(R)) != HB_OK) bad = HB_ERR_CUDA;
+            t_up[d] = now_s() - t0;
+        });
+    const double t_al0 = now_s();
+    rc = hbh_alns_load(alns_dir, R, core, n_core, io_threads, &A);
+    const double t_ingest = now_s() - t_al0;
+    const std::string ingest_err = rc ? t_err : std::string();
+    for (auto& t : dev_th) t.join();
+    if (rc) { t_err = ingest_err; cleanup(); return rc; }
+    if (bad.load()) {
+        t_err = "context creation / read-store upload failed";
+        for (hb_ctx* c : ctx) if (c) { t_err += std::string(": ") + hb_last_error(c); break; }
+        if (const char* ce = hb_last_error(nullptr)) if (*ce) t_err += std::string(": ") + ce;
+        cleanup();
+        return bad.load();
     }
     hbh_fasta* W = nullptr;
     rc = hbh_fasta_open(output, &W);
